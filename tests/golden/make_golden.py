@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures under tests/golden/ from the reference tree.
+
+Runs ONLY in the build container (needs /root/reference); the GPU box never has the reference,
+so everything the tests need is written to small .npz files that are committed next to this script.
+
+Sources (all paths relative to /root/reference):
+  * benchmark/data/lasso_{tiny,small,medium}.jld2  -- HDF5-in-JLD2 fixtures (A, b, lambda, xstar, ystar).
+    No HDF5 reader exists in this image, so the little-endian f64 payloads are read at the byte offsets
+    established in SURVEY.md section 8c; each file's sha256 prefix is asserted so a different file cannot
+    be mis-read silently.
+  * test/problems/test_lasso_small.jl:17-23,42  -- literal 4x5 A, b and x_star.
+  * test/problems/test_lasso_small_strongly_convex.jl:11-44,53 -- literal w, B, x_star; A = Q D Q',
+    b = A x* + lam inv(A') sign(x*), x0 = A \\ b are re-derived with LAPACK exactly as the test does.
+The literals are parsed out of the .jl files with regular expressions (nothing is copied by hand).
+"""
+import hashlib
+import os
+import re
+import sys
+
+import numpy as np
+
+REF = os.environ.get("PROX_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# name: (rows, cols, off_A, off_ystar, off_b, off_lambda, off_xstar, sha256[:16])
+JLD2 = {
+    "tiny": (5, 10, 630, 1095, 1200, 1289, 1362, "b5231e9c4c793d64"),
+    "small": (50, 100, 647, 40709, 41175, 41624, 41698, "9dd5ab8fc9720ac1"),
+    "medium": (500, 1000, 647, 4000709, 4004775, 4008824, 4008898, "253e738baaa339cd"),
+}
+
+
+def read_jld2(name):
+    m, n, o_a, o_y, o_b, o_l, o_x, sha = JLD2[name]
+    path = os.path.join(REF, "benchmark", "data", f"lasso_{name}.jld2")
+    buf = open(path, "rb").read()
+    got = hashlib.sha256(buf).hexdigest()[:16]
+    if got != sha:
+        raise SystemExit(f"{path}: sha256 {got} != expected {sha}; offsets would be wrong")
+    a = np.frombuffer(buf, "<f8", m * n, o_a).reshape(n, m).T  # Julia column-major
+    return dict(
+        A=np.asfortranarray(a),
+        b=np.frombuffer(buf, "<f8", m, o_b).copy(),
+        ystar=np.frombuffer(buf, "<f8", m, o_y).copy(),
+        xstar=np.frombuffer(buf, "<f8", n, o_x).copy(),
+        lam=np.float64(np.frombuffer(buf, "<i8", 1, o_l)[0]),
+    )
+
+
+_NUM = r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?"
+
+
+def _block_after(text, marker):
+    """Return the text between the '[' that follows `marker` and its closing ']'."""
+    i = text.index(marker)
+    i = text.index("[", i)
+    j = text.index("]", i)
+    return text[i + 1 : j]
+
+
+def _matrix(block):
+    rows = [r for r in block.strip().splitlines() if r.strip()]
+    return np.array([[float(t) for t in re.findall(_NUM, r)] for r in rows], dtype=np.float64)
+
+
+def _vector(block):
+    return np.array([float(t) for t in re.findall(_NUM, block)], dtype=np.float64)
+
+
+def unit_lasso_4x5():
+    src = open(os.path.join(REF, "test", "problems", "test_lasso_small.jl")).read()
+    a = _matrix(_block_after(src, "A = T["))
+    b = _vector(_block_after(src, "b = T["))
+    xs = _vector(_block_after(src, "x_star = T["))
+    assert a.shape == (4, 5) and b.shape == (4,) and xs.shape == (5,)
+    return dict(A=np.asfortranarray(a), b=b, xstar=xs)
+
+
+def unit_lasso_sc_5x5():
+    src = open(os.path.join(REF, "test", "problems", "test_lasso_small_strongly_convex.jl")).read()
+    xs = _vector(_block_after(src, "x_star = T["))
+    w = _vector(_block_after(src, "w = T["))
+    bmat = _matrix(_block_after(src, "B = T["))
+    assert xs.shape == (5,) and w.shape == (5,) and bmat.shape == (5, 5)
+    mf, lf = 1.0, 10.0
+    lam = (mf + lf) / 2
+    d = np.sqrt(mf) + (np.sqrt(lf) - np.sqrt(mf)) * w
+    d[0] = np.sqrt(mf)
+    d[-1] = np.sqrt(lf)
+    q, _ = np.linalg.qr(bmat)
+    a = q @ np.diag(d) @ q.T
+    b = a @ xs + lam * np.linalg.solve(a.T, np.sign(xs))
+    x0 = np.linalg.solve(a, b)
+    return dict(A=np.asfortranarray(a), b=b, xstar=xs, x0=x0, lam=np.float64(lam), mf=np.float64(mf), Lf=np.float64(lf))
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit(f"{REF} not present: golden fixtures can only be regenerated in the build container")
+    for name in JLD2:
+        d = read_jld2(name)
+        np.savez_compressed(os.path.join(OUT, f"lasso_{name}.npz"), **d)
+        r = d["A"] @ d["xstar"] - d["b"]
+        print(f"lasso_{name}: A{d['A'].shape} lam={d['lam']} obj(x*)={0.5 * r @ r + d['lam'] * np.abs(d['xstar']).sum():.16g}")
+    np.savez_compressed(os.path.join(OUT, "unit_lasso_4x5.npz"), **unit_lasso_4x5())
+    np.savez_compressed(os.path.join(OUT, "unit_lasso_sc_5x5.npz"), **unit_lasso_sc_5x5())
+    print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
+
+
+if __name__ == "__main__":
+    main()
