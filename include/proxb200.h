@@ -1,0 +1,171 @@
+/*
+ * proxb200.h -- C ABI of libproxb200.so: the B200-native proximal-gradient hot path.
+ *
+ * The reference (ProximalAlgorithms.jl v0.7.0, pure Julia) has NO FFI boundary of its own; its plug-in surface
+ * is method extension on array/functional types.  The entry points below are exactly what a
+ * `ccall` shim specialising the reference's iterators on a device-vector type binds; every function cites the
+ * reference arithmetic it replaces (paths relative to the reference tree, abbreviated:
+ *   FFB = src/algorithms/fast_forward_backward.jl, FB = src/algorithms/forward_backward.jl,
+ *   FBT = src/utilities/fb_tools.jl, BM = benchmark/benchmarks.jl).
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md and shipped in
+ * proximalalgorithms.jl_b200/julia/B200Prox.jl.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, doubles.  No torch / C++ types cross this boundary.
+ *   - every function returns 0 on success, a PB_E* code otherwise; pb_last_error() gives the message (thread local).
+ *   - device pointers are raw CUDA device addresses on the context's device (from pb_malloc, cudaMalloc or
+ *     tensor.data_ptr()); `dtype` selects float / double for every vector argument of the call.
+ *   - kernels are enqueued on the context's stream and return immediately.  Reduction results are left in the context's
+ *     device scalar block (PB_NSCALARS doubles); pb_read_scalars() copies it to the host and synchronises -- that is the
+ *     one host sync per iteration the reference's driver loop needs (src/ProximalAlgorithms.jl:116-120).
+ *   - scalar parameters (gamma, beta, lambda...) are passed as double and narrowed to `dtype` on entry; callers that
+ *     keep their scalars in R = real(eltype(x0)) (as the reference does) lose nothing in the widening.
+ *   - one host thread per context.  The library never calls back into the host language.
+ */
+#ifndef PROXB200_H
+#define PROXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_VERSION_STRING "0.1.0"
+
+/* ---- status codes -------------------------------------------------------------------------------------------- */
+enum {
+  PB_OK = 0,
+  PB_EINVAL = 1,   /* bad argument (null pointer, negative size, unknown dtype/prox kind, misaligned group...) */
+  PB_ECUDA = 2,    /* a CUDA runtime call or kernel launch failed; message carries cudaGetErrorString */
+  PB_ENOMEM = 3,   /* host or device allocation failed */
+  PB_EUNSUPPORTED = 4
+};
+
+/* ---- element types --------------------------------------------------------------------------------------------- */
+enum { PB_F32 = 0, PB_F64 = 1 };
+
+/* ---- proximable terms (ProximalOperators.jl semantics; call sites FFB:80,141  FB:72,118  FBT:49) ---------------- */
+enum {
+  PB_PROX_ZERO = 0,    /* ProximalCore.Zero: identity prox, value 0                                   */
+  PB_PROX_L1 = 1,      /* NormL1(lambda): soft threshold, value lambda*||z||_1   (BM:52,60)               */
+  PB_PROX_BOX = 2,     /* IndBox(lo,hi): clamp, value 0  (test/problems/test_nonconvex_qp.jl:19,33)       */
+  PB_PROX_SCALE = 3,   /* z = s*y with a caller-supplied factor: phase 2 of IndBallL2 (s = min(1, r/||y||)) */
+  PB_PROX_L21 = 4      /* NormL21(lambda, dim=1) on contiguous groups of `group` elements                  */
+};
+
+typedef struct pb_prox {
+  int32_t kind;        /* PB_PROX_*                                                                        */
+  int32_t group;       /* PB_PROX_L21: group length (elements); otherwise ignored                          */
+  double p0;           /* L1/L21: lambda;  BOX: lo (used when v0 == NULL);  SCALE: s                        */
+  double p1;           /* BOX: hi (used when v1 == NULL)                                                   */
+  const void* v0;      /* BOX: optional per-element lower bounds (device, same dtype as the vectors)        */
+  const void* v1;      /* BOX: optional per-element upper bounds                                            */
+} pb_prox;
+
+/* ---- device scalar block layout --------------------------------------------------------------------------------
+ * Sums are accumulated as double-double (hi, lo) with error-free transformations so that the rounded result does not
+ * depend on grid size or on how a vector is sharded across GPUs (hard part 1).  A consumer adds the
+ * pairs of all shards in double-double and rounds once: value = hi + lo.
+ */
+enum {
+  PB_S_GSUM = 0,      /* [0],[1]  hi,lo of  sum|z_i| (L1),  sum_g scal_g*||y_g|| (L21), 0 otherwise; g(z) = lambda*that */
+  PB_S_RESSQ = 2,     /* [2],[3]  sum (x_i - z_i)^2                 -> norm(res)^2 of FBT:4                         */
+  PB_S_GDR = 4,       /* [4],[5]  sum grad_i*(x_i - z_i)            -> dot(grad_f_x, res) of FBT:4                  */
+  PB_S_RESINF = 6,    /* [6]      max |x_i - z_i| (NaN propagates)  -> norm(res, Inf) of FB:125-126, FFB:147-152    */
+  PB_S_AUX = 8,       /* [8],[9]  kernel-specific sum: ||y||^2 (pb_forward), ||v||^2 (pb_nrm2sq), <a,b> (pb_dot),
+                                  ||A x - b||^2 (pb_lsq_*_residual), ||x - b||^2 (pb_sqdist)                        */
+  PB_S_AUXINF = 10,   /* [10]     kernel-specific max: max|v_i| (pb_norm_inf)                                       */
+  PB_NSCALARS = 16
+};
+
+typedef struct pb_ctx pb_ctx;
+
+/* ---- library / context ----------------------------------------------------------------------------------------- */
+const char* pb_version(void);
+const char* pb_last_error(void);
+int pb_device_count(int* count);
+
+/* Create a context on CUDA device `device`.  borrow_stream != 0: `stream` is an existing cudaStream_t the context
+ * borrows (e.g. torch's current stream; NULL is the legacy default stream).  borrow_stream == 0: `stream` is ignored
+ * and the context creates and owns a non-blocking stream. */
+int pb_ctx_create(int device, void* stream, int borrow_stream, pb_ctx** out);
+int pb_ctx_destroy(pb_ctx* ctx);
+void* pb_ctx_stream(pb_ctx* ctx);
+int pb_ctx_sync(pb_ctx* ctx);
+/* Device address of the PB_NSCALARS-double scalar block (so a host framework can all-gather it in place). */
+double* pb_ctx_scalars_dev(pb_ctx* ctx);
+/* Redirect the scalar block to caller-owned device memory (PB_NSCALARS doubles, e.g. a framework tensor that is the
+ * send buffer of the per-iteration all-gather).  NULL restores the context's own block. */
+int pb_ctx_set_scalars_dev(pb_ctx* ctx, double* dev);
+/* Launch shape knobs (0 keeps the default): CTAs per SM for streaming kernels; streaming cache hints on/off (-1 = auto by size). */
+int pb_ctx_set_launch(pb_ctx* ctx, int ctas_per_sm, int stream_hints);
+/* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
+int64_t pb_ctx_launch_count(pb_ctx* ctx);
+
+/* ---- memory (lets a host without a CUDA binding own device vectors: Julia `B200Vector`) -------------------------- */
+int pb_malloc(pb_ctx* ctx, size_t bytes, void** dptr);
+int pb_free(pb_ctx* ctx, void* dptr);
+int pb_host_alloc(size_t bytes, void** hptr);                /* pinned host memory */
+int pb_host_free(void* hptr);
+int pb_upload(pb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);    /* async on the ctx stream */
+int pb_download(pb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* synchronises */
+int pb_copy(pb_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);       /* `copy`, FFB:74, FB:66 */
+int pb_memset_zero(pb_ctx* ctx, void* dst_dev, size_t bytes);                     /* `zero(x)` */
+/* Copy the device scalar block to `out` (PB_NSCALARS doubles) and synchronise the stream. */
+int pb_read_scalars(pb_ctx* ctx, double* out);
+
+/* ---- K1: fused forward-backward step ------------------------------------------------------------------------------
+ * One pass:  y = x - gamma*grad (FB:117, FFB:140, FBT:48);  z = prox_{gamma g}(y) (FB:118, FFB:141, FBT:49);
+ * res = x - z (FB:120, FFB:142, FBT:50);  reductions GSUM, RESSQ, GDR (f_model, FBT:3-5) and RESINF (stop rule).
+ * `y` and `res` may be NULL (not materialised).  mul and add are rounded separately (no FMA contraction), as Julia's
+ * broadcast does.  Algorithmic traffic: 3 vectors (read x, grad; write z). */
+int pb_fb_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, double gamma, const pb_prox* g,
+               void* y, void* z, void* res);
+
+/* ---- K2: K1 plus the next iteration's extrapolation in the same pass ---------------------------------------------
+ * x_next = z + beta*(z - z_prev) (FFB:135), where z_prev is the previous forward-backward point.  x_next must not
+ * alias x.  Algorithmic traffic: 5 vectors (read x, grad, z_prev; write z, x_next). */
+int pb_ffb_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev, double gamma,
+                double beta, const pb_prox* g, void* y, void* z, void* res, void* x_next);
+
+/* ---- K3: standalone prox (init `prox(g, y, gamma)` FFB:80, FB:72; user-driven splittings) ------------------------- */
+int pb_prox_apply(pb_ctx* ctx, int dtype, int64_t n, const void* y, double gamma, const pb_prox* g, void* z);
+/* y = x - gamma*grad and AUX = ||y||^2 : phase 1 of IndBallL2 (needs the global norm before scaling). */
+int pb_forward(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, double gamma, void* y);
+
+/* ---- K6: vector utilities (unfused path, lazy state fields) ------------------------------------------------------- */
+int pb_extrapolate(pb_ctx* ctx, int dtype, int64_t n, const void* z, const void* z_prev, double beta, void* x); /* FFB:135 */
+int pb_residual(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* z, const void* grad_or_null,
+                void* res);                             /* res = x - z with RESSQ, RESINF (+GDR when grad given) */
+int pb_add_scalar(pb_ctx* ctx, int dtype, int64_t n, const void* x, double c, void* out);   /* x .+ 1, FBT:9 */
+int pb_sub(pb_ctx* ctx, int dtype, int64_t n, const void* a, const void* b, void* out);     /* a - b;  AUX = ||a-b||^2 (FBT:11) */
+int pb_nrm2sq(pb_ctx* ctx, int dtype, int64_t n, const void* v);                             /* AUX = sum v^2, AUXINF = max|v| */
+int pb_dot(pb_ctx* ctx, int dtype, int64_t n, const void* a, const void* b);                 /* AUX = sum a*b */
+
+/* ---- K4: least-squares smooth term  f(x) = 0.5*||A x - b||^2  (BM:11-17) ------------------------------------------
+ * dense: A column-major m x n with leading dimension lda (Julia Matrix).  residual: r = A x - b, AUX = ||r||^2.
+ * gradient: grad = A' r.  `b` may be NULL (r = A x: partial product of a column shard). */
+int pb_lsq_dense_residual(pb_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, int64_t lda, const void* x,
+                          const void* b, void* r);
+int pb_lsq_dense_gradient(pb_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, int64_t lda, const void* r,
+                          void* grad);
+/* block-diagonal ("implicit A via batched GEMV", BASELINE.json configs[1]): nblk blocks, block k is a column-major
+ * mb x nb matrix at A + k*mb*nb; x has nblk*nb entries, r/b have nblk*mb. */
+int pb_lsq_blockdiag_residual(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, int64_t nb, const void* A,
+                              const void* x, const void* b, void* r);
+int pb_lsq_blockdiag_gradient(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, int64_t nb, const void* A,
+                              const void* r, void* grad);
+/* SquaredDistance (BM:19-28): grad = x - b, AUX = ||x - b||^2. */
+int pb_sqdist(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* b, void* grad);
+
+/* ---- host-buffer convenience (the "plugin call with HOST buffers"): upload x, grad, z_prev, run K2, download z, x_next
+ * and the scalar block.  All host pointers; temporary device buffers are cached in the context. */
+int pb_ffb_step_host(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev,
+                     double gamma, double beta, const pb_prox* g, void* z, void* x_next, double* scalars);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROXB200_H */

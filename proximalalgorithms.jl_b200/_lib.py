@@ -1,0 +1,104 @@
+"""ctypes binding of libproxb200.so (declared in include/proxb200.h).
+
+The library is the product: there is no Python / torch / CPU fallback for any entry point.  If the shared object is
+missing (not built) the import of this module raises immediately with the build command.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libproxb200.so")
+
+PB_F32, PB_F64 = 0, 1
+PB_PROX_ZERO, PB_PROX_L1, PB_PROX_BOX, PB_PROX_SCALE, PB_PROX_L21 = 0, 1, 2, 3, 4
+PB_S_GSUM, PB_S_RESSQ, PB_S_GDR, PB_S_RESINF, PB_S_AUX, PB_S_AUXINF, PB_NSCALARS = 0, 2, 4, 6, 8, 10, 16
+
+
+class ProxB200Error(RuntimeError):
+    """Raised when a libproxb200 call returns a non-zero status (message from pb_last_error)."""
+
+
+class pb_prox(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("group", C.c_int32),
+        ("p0", C.c_double),
+        ("p1", C.c_double),
+        ("v0", C.c_void_p),
+        ("v1", C.c_void_p),
+    ]
+
+
+_vp, _i, _i64, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
+_pp = C.POINTER(pb_prox)
+
+# name -> (restype, argtypes); mirrors include/proxb200.h one to one (tests/test_abi.py checks the header against this table)
+SIGNATURES = {
+    "pb_version": (C.c_char_p, []),
+    "pb_last_error": (C.c_char_p, []),
+    "pb_device_count": (_i, [C.POINTER(C.c_int)]),
+    "pb_ctx_create": (_i, [_i, _vp, _i, C.POINTER(_vp)]),
+    "pb_ctx_destroy": (_i, [_vp]),
+    "pb_ctx_stream": (_vp, [_vp]),
+    "pb_ctx_sync": (_i, [_vp]),
+    "pb_ctx_scalars_dev": (_vp, [_vp]),
+    "pb_ctx_set_scalars_dev": (_i, [_vp, _vp]),
+    "pb_ctx_set_launch": (_i, [_vp, _i, _i]),
+    "pb_ctx_launch_count": (_i64, [_vp]),
+    "pb_malloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "pb_free": (_i, [_vp, _vp]),
+    "pb_host_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "pb_host_free": (_i, [_vp]),
+    "pb_upload": (_i, [_vp, _vp, _vp, _sz]),
+    "pb_download": (_i, [_vp, _vp, _vp, _sz]),
+    "pb_copy": (_i, [_vp, _vp, _vp, _sz]),
+    "pb_memset_zero": (_i, [_vp, _vp, _sz]),
+    "pb_read_scalars": (_i, [_vp, C.POINTER(C.c_double)]),
+    "pb_fb_step": (_i, [_vp, _i, _i64, _vp, _vp, _d, _pp, _vp, _vp, _vp]),
+    "pb_ffb_step": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _d, _d, _pp, _vp, _vp, _vp, _vp]),
+    "pb_prox_apply": (_i, [_vp, _i, _i64, _vp, _d, _pp, _vp]),
+    "pb_forward": (_i, [_vp, _i, _i64, _vp, _vp, _d, _vp]),
+    "pb_extrapolate": (_i, [_vp, _i, _i64, _vp, _vp, _d, _vp]),
+    "pb_residual": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
+    "pb_add_scalar": (_i, [_vp, _i, _i64, _vp, _d, _vp]),
+    "pb_sub": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "pb_nrm2sq": (_i, [_vp, _i, _i64, _vp]),
+    "pb_dot": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "pb_lsq_dense_residual": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "pb_lsq_dense_gradient": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "pb_lsq_blockdiag_residual": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "pb_lsq_blockdiag_gradient": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "pb_sqdist": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "pb_ffb_step_host": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _d, _d, _pp, _vp, _vp, C.POINTER(C.c_double)]),
+}
+
+
+def load(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise ProxB200Error(
+            f"{path} not found: the CUDA library is the product and has no fallback. "
+            "Build it with `python proximalalgorithms.jl_b200/build.py` (needs nvcc)."
+        )
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = load()
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise ProxB200Error(f"libproxb200 error {rc}: {lib().pb_last_error().decode(errors='replace')}")

@@ -1,0 +1,38 @@
+"""Public names (the reference module exports nothing and is used as `ProximalAlgorithms.X`; same here: `proxb200.X`)."""
+from ._lib import LIB_PATH, ProxB200Error  # noqa: F401
+from .algorithms import (  # noqa: F401
+    FastForwardBackward,
+    FastForwardBackwardIteration,
+    FastForwardBackwardState,
+    FastProximalGradient,
+    FastProximalGradientIteration,
+    ForwardBackward,
+    ForwardBackwardIteration,
+    ForwardBackwardState,
+    IterativeAlgorithm,
+    ProximalGradient,
+    ProximalGradientIteration,
+    default_display,
+    default_solution,
+    default_stopping_criterion,
+)
+from .functions import (  # noqa: F401
+    BlockDiagLeastSquares,
+    IndBallL2,
+    IndBox,
+    LeastSquares,
+    LinearFunction,
+    NormL1,
+    NormL21,
+    SquaredDistance,
+    Zero,
+)
+from .host import Context, LocalComm, Scalars, TorchDistComm, shard_bounds  # noqa: F401
+from .nesterov import (  # noqa: F401
+    AdaptiveNesterovSequence,
+    ConstantNesterovSequence,
+    FixedNesterovSequence,
+    SimpleNesterovSequence,
+)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

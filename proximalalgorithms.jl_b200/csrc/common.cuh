@@ -1,0 +1,293 @@
+// common.cuh -- shared device helpers for libproxb200 (sm_100a).
+//   * context definition
+//   * double-double accumulation (error-free transformations) and the deterministic block -> grid reduction
+//   * 16-byte packed loads/stores with optional streaming cache hints
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "proxb200.h"
+
+#define PB_BLOCK 256            // threads per CTA of every streaming kernel
+#define PB_MAX_CTAS 4096        // upper bound on grid size of reducing kernels (workspace rows)
+#define PB_MAX_SUMS 4           // double-double sums a kernel may reduce
+#define PB_MAX_MAXS 2           // max-reductions a kernel may reduce
+
+// Reduction workspace in device memory: a ticket counter and per-CTA partials laid out [quantity][cta].
+struct PbWorkspace {
+  unsigned int ticket;
+  unsigned int pad[63];
+  double sum_hi[PB_MAX_SUMS][PB_MAX_CTAS];
+  double sum_lo[PB_MAX_SUMS][PB_MAX_CTAS];
+  double mx[PB_MAX_MAXS][PB_MAX_CTAS];
+};
+
+struct pb_ctx {
+  int device;
+  cudaStream_t stream;
+  bool owns_stream;
+  int sm_count;
+  size_t l2_bytes;
+  int ctas_per_sm;     // 0 = per-kernel default
+  int stream_hints;    // -1 auto, 0 off, 1 on
+  double* scalars_dev;   // active scalar block (own or caller supplied)
+  double* scalars_own;
+  double* scalars_host;  // pinned mirror
+  PbWorkspace* ws;
+  int64_t launches;
+  // scratch for the dense / block-diagonal products (partial sums of column chunks)
+  void* scratch;
+  size_t scratch_bytes;
+  // cached device buffers of pb_ffb_step_host
+  void* hbuf[5];
+  size_t hbuf_bytes;
+};
+
+void pb_set_error(const char* fmt, ...);
+int pb_ensure_scratch(pb_ctx* ctx, size_t bytes);
+
+#define PB_CHECK_CUDA(call)                                                                    \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      pb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));      \
+      return PB_ECUDA;                                                                         \
+    }                                                                                          \
+  } while (0)
+
+#define PB_REQUIRE(cond, msg)                                  \
+  do {                                                         \
+    if (!(cond)) {                                             \
+      pb_set_error("%s: %s", __func__, msg);                   \
+      return PB_EINVAL;                                        \
+    }                                                          \
+  } while (0)
+
+#define PB_LAUNCH_CHECK(ctx)                                   \
+  do {                                                         \
+    (ctx)->launches++;                                         \
+    PB_CHECK_CUDA(cudaGetLastError());                         \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// rounding-exact scalar arithmetic: Julia broadcasts `x .- gamma .* g` round the product and the difference
+// separately (no muladd in the reference), so the intrinsics below are used to forbid FMA contraction.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// double-double accumulator
+// ---------------------------------------------------------------------------------------------------------------
+struct dd {
+  double hi, lo;
+};
+
+// a += v  (Knuth two-sum into hi, error into lo)
+__device__ __forceinline__ void dd_add(dd& a, double v) {
+  double s = __dadd_rn(a.hi, v);
+  double bb = __dsub_rn(s, a.hi);
+  double e = __dadd_rn(__dsub_rn(a.hi, __dsub_rn(s, bb)), __dsub_rn(v, bb));
+  a.hi = s;
+  a.lo = __dadd_rn(a.lo, e);
+}
+// a += p*q exactly (two-prod via FMA)
+__device__ __forceinline__ void dd_add_prod(dd& a, double p, double q) {
+  double pr = __dmul_rn(p, q);
+  double er = __fma_rn(p, q, -pr);
+  dd_add(a, pr);
+  a.lo = __dadd_rn(a.lo, er);
+}
+// a + b for two double-doubles, renormalised
+__device__ __forceinline__ dd dd_sum(const dd& a, const dd& b) {
+  double s = __dadd_rn(a.hi, b.hi);
+  double bb = __dsub_rn(s, a.hi);
+  double e = __dadd_rn(__dsub_rn(a.hi, __dsub_rn(s, bb)), __dsub_rn(b.hi, bb));
+  e = __dadd_rn(e, __dadd_rn(a.lo, b.lo));
+  dd r;
+  r.hi = __dadd_rn(s, e);                       // fast two-sum renormalisation
+  r.lo = __dsub_rn(e, __dsub_rn(r.hi, s));
+  return r;
+}
+
+// NaN-propagating max of non-negative values (Julia's norm(., Inf) returns NaN if any entry is NaN)
+__device__ __forceinline__ double nanmax(double m, double a) { return (a > m || a != a) ? a : m; }
+
+template <int NSUM, int NMAX>
+struct Acc {
+  dd s[NSUM > 0 ? NSUM : 1];
+  double m[NMAX > 0 ? NMAX : 1];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < (NSUM > 0 ? NSUM : 1); ++k) s[k].hi = s[k].lo = 0.0;
+#pragma unroll
+    for (int k = 0; k < (NMAX > 0 ? NMAX : 1); ++k) m[k] = 0.0;
+  }
+};
+
+struct OutMap {
+  int sum_slot[PB_MAX_SUMS];  // index into the scalar block of the hi word (lo = +1); -1 = discard
+  int max_slot[PB_MAX_MAXS];
+};
+
+__device__ __forceinline__ double shfl_down_d(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+
+template <int NSUM, int NMAX>
+__device__ __forceinline__ void warp_reduce(Acc<NSUM, NMAX>& a) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) {
+      dd o;
+      o.hi = shfl_down_d(a.s[k].hi, off);
+      o.lo = shfl_down_d(a.s[k].lo, off);
+      a.s[k] = dd_sum(a.s[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) a.m[k] = nanmax(a.m[k], shfl_down_d(a.m[k], off));
+  }
+}
+
+// Reduce the per-thread accumulators of one CTA; result valid in thread 0.  BLOCK must be a multiple of 32, <= 1024.
+template <int NSUM, int NMAX, int BLOCK>
+__device__ __forceinline__ void block_reduce(Acc<NSUM, NMAX>& a) {
+  constexpr int NW = BLOCK / 32;
+  __shared__ double sh_hi[NSUM > 0 ? NSUM : 1][NW];
+  __shared__ double sh_lo[NSUM > 0 ? NSUM : 1][NW];
+  __shared__ double sh_mx[NMAX > 0 ? NMAX : 1][NW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  warp_reduce<NSUM, NMAX>(a);
+  __syncthreads();  // protects reuse of the shared arrays when called twice
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) {
+      sh_hi[k][warp] = a.s[k].hi;
+      sh_lo[k][warp] = a.s[k].lo;
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) sh_mx[k][warp] = a.m[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) {
+      a.s[k].hi = lane < NW ? sh_hi[k][lane] : 0.0;
+      a.s[k].lo = lane < NW ? sh_lo[k][lane] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) a.m[k] = lane < NW ? sh_mx[k][lane] : 0.0;
+    warp_reduce<NSUM, NMAX>(a);
+  }
+}
+
+// CTA partial -> workspace; the last CTA to arrive folds all partials in a fixed order (deterministic for a given
+// grid, and -- thanks to the double-double arithmetic -- equal after rounding for any grid) and writes the scalar block.
+template <int NSUM, int NMAX, int BLOCK>
+__device__ __forceinline__ void grid_reduce(Acc<NSUM, NMAX>& a, PbWorkspace* ws, double* out, const OutMap& map) {
+  __shared__ bool is_last;
+  block_reduce<NSUM, NMAX, BLOCK>(a);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) {
+      ws->sum_hi[k][blockIdx.x] = a.s[k].hi;
+      ws->sum_lo[k][blockIdx.x] = a.s[k].lo;
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) ws->mx[k][blockIdx.x] = a.m[k];
+    __threadfence();
+    unsigned int t = atomicAdd(&ws->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  a.clear();
+  for (unsigned int c = threadIdx.x; c < gridDim.x; c += BLOCK) {
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) {
+      dd o;
+      o.hi = __ldcg(&ws->sum_hi[k][c]);
+      o.lo = __ldcg(&ws->sum_lo[k][c]);
+      a.s[k] = dd_sum(a.s[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) a.m[k] = nanmax(a.m[k], __ldcg(&ws->mx[k][c]));
+  }
+  block_reduce<NSUM, NMAX, BLOCK>(a);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k)
+      if (map.sum_slot[k] >= 0) {
+        out[map.sum_slot[k]] = a.s[k].hi;
+        out[map.sum_slot[k] + 1] = a.s[k].lo;
+      }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k)
+      if (map.max_slot[k] >= 0) out[map.max_slot[k]] = a.m[k];
+    ws->ticket = 0;  // ready for the next launch on this stream
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// packed 16-byte global memory access
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) Pack {
+  T v[VEC];
+};
+
+template <typename T, int VEC, bool HINT>
+__device__ __forceinline__ Pack<T, VEC> ld_pack(const T* p) {
+  Pack<T, VEC> r;
+  if constexpr (sizeof(T) * VEC == 16) {
+    float4 t = HINT ? __ldcs(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p));
+    *reinterpret_cast<float4*>(&r) = t;
+  } else {
+    static_assert(VEC == 1, "only 16-byte packs or scalars");
+    r.v[0] = HINT ? __ldcs(p) : __ldg(p);
+  }
+  return r;
+}
+
+template <typename T, int VEC, bool HINT>
+__device__ __forceinline__ void st_pack(T* p, const Pack<T, VEC>& r) {
+  if constexpr (sizeof(T) * VEC == 16) {
+    if (HINT)
+      __stcs(reinterpret_cast<float4*>(p), *reinterpret_cast<const float4*>(&r));
+    else
+      *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(&r);
+  } else {
+    if (HINT)
+      __stcs(p, r.v[0]);
+    else
+      *p = r.v[0];
+  }
+}
+
+// host-side single rounding product in the element type (gamma*lambda is formed in R by the reference)
+static inline float mul_rn_host(float a, float b) {
+  volatile float r = a * b;
+  return r;
+}
+static inline double mul_rn_host(double a, double b) {
+  volatile double r = a * b;
+  return r;
+}
+
+static inline bool pb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// default grid for a grid-stride streaming kernel
+static inline int pb_stream_grid(const pb_ctx* ctx, int64_t work_items_per_cta, int64_t n, int default_ctas_per_sm) {
+  int per_sm = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : default_ctas_per_sm;
+  int64_t g = (int64_t)ctx->sm_count * per_sm;
+  int64_t need = (n + work_items_per_cta - 1) / work_items_per_cta;
+  if (need < 1) need = 1;
+  if (g > need) g = need;
+  if (g > PB_MAX_CTAS) g = PB_MAX_CTAS;
+  return (int)g;
+}

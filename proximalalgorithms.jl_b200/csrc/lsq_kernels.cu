@@ -1,0 +1,213 @@
+// lsq_kernels.cu -- K4: value and gradient of the least-squares smooth term f(x) = 0.5*||A x - b||^2
+// (benchmark/benchmarks.jl:11-17: `res = A*x - b; norm(res)^2/2, A'*res`), dense column-major and block-diagonal.
+//
+// A single-right-hand-side product has 0.5 (fp32) / 0.25 (fp64) flop per byte of A: it is HBM (or, for the small
+// benchmark fixtures, L2/latency) bound and there is no tensor-core formulation that would not change the arithmetic,
+// so both products are plain coalesced streaming kernels with fixed-order (deterministic) accumulation:
+//   residual : thread per row, column range split into chunks (grid.y) and 4 column lanes per CTA; chunk partials are
+//              folded in index order by a second kernel that also subtracts b and reduces ||r||^2 (double-double).
+//   gradient : warp per column (columns are contiguous), lanes stride over rows, shuffle tree.
+#include "common.cuh"
+
+#define GEMV_ROWS 128  // rows per CTA of the residual kernel
+#define GEMV_CL 4      // column lanes per CTA
+#define GEMV_UNROLL 8
+
+// partial[(chunk*nblk + k)*mb + i] = sum_{j in chunk} A_k[i, j] * x_k[j]
+template <typename T>
+__global__ void __launch_bounds__(GEMV_ROWS* GEMV_CL)
+    k_gemv_n_partial(const T* __restrict__ A, int64_t lda, int64_t blk_stride, const T* __restrict__ x,
+                     T* __restrict__ partial, int64_t mb, int64_t nb, int64_t nblk, int64_t chunk_cols) {
+  __shared__ T sh[GEMV_CL][GEMV_ROWS];
+  const int rl = threadIdx.x % GEMV_ROWS, cl = threadIdx.x / GEMV_ROWS;
+  const int64_t k = blockIdx.z;
+  const int64_t row = (int64_t)blockIdx.x * GEMV_ROWS + rl;
+  const int64_t c0 = (int64_t)blockIdx.y * chunk_cols;
+  int64_t c1 = c0 + chunk_cols;
+  if (c1 > nb) c1 = nb;
+  const T* __restrict__ Ak = A + k * blk_stride;
+  const T* __restrict__ xk = x + k * nb;
+  T acc = T(0);
+  if (row < mb) {
+    int64_t j = c0 + cl;
+    // UNROLL independent loads in flight per thread
+    for (; j + (GEMV_UNROLL - 1) * GEMV_CL < c1; j += GEMV_UNROLL * GEMV_CL) {
+      T a[GEMV_UNROLL], xv[GEMV_UNROLL];
+#pragma unroll
+      for (int u = 0; u < GEMV_UNROLL; ++u) {
+        a[u] = __ldg(Ak + row + (j + u * GEMV_CL) * lda);
+        xv[u] = __ldg(xk + j + u * GEMV_CL);
+      }
+#pragma unroll
+      for (int u = 0; u < GEMV_UNROLL; ++u) acc = fma(a[u], xv[u], acc);
+    }
+    for (; j < c1; j += GEMV_CL) acc = fma(__ldg(Ak + row + j * lda), __ldg(xk + j), acc);
+  }
+  sh[cl][rl] = acc;
+  __syncthreads();
+  if (cl == 0 && row < mb) {
+    T s = sh[0][rl];
+#pragma unroll
+    for (int c = 1; c < GEMV_CL; ++c) s += sh[c][rl];
+    partial[((int64_t)blockIdx.y * nblk + k) * mb + row] = s;
+  }
+}
+
+// r[i] = (sum_chunks partial[c][i]) - b[i];  AUX = sum r^2
+template <typename T>
+__global__ void __launch_bounds__(PB_BLOCK) k_gemv_n_combine(const T* __restrict__ partial, int nchunk, int64_t M,
+                                                             const T* __restrict__ b, T* __restrict__ r,
+                                                             PbWorkspace* ws, double* outs) {
+  constexpr bool COMP = sizeof(T) == 8;
+  Acc<1, 1> acc;
+  acc.clear();
+  for (int64_t i = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < M; i += (int64_t)gridDim.x * PB_BLOCK) {
+    T s = partial[i];
+    for (int c = 1; c < nchunk; ++c) s += partial[(int64_t)c * M + i];
+    const T rv = b ? sub_rn(s, b[i]) : s;
+    r[i] = rv;
+    if (COMP)
+      dd_add_prod(acc.s[0], (double)rv, (double)rv);
+    else
+      acc.s[0].hi = __fma_rn((double)rv, (double)rv, acc.s[0].hi);
+  }
+  OutMap map;
+  map.sum_slot[0] = PB_S_AUX;
+  map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
+  map.max_slot[0] = map.max_slot[1] = -1;
+  grid_reduce<1, 1, PB_BLOCK>(acc, ws, outs, map);
+}
+
+// grad[k*nb + j] = sum_i A_k[i, j] * r[k*mb + i]   (warp per column)
+template <typename T>
+__global__ void __launch_bounds__(PB_BLOCK) k_gemv_t(const T* __restrict__ A, int64_t lda, int64_t blk_stride,
+                                                     const T* __restrict__ r, T* __restrict__ grad, int64_t mb,
+                                                     int64_t nb, int64_t nblk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * PB_BLOCK + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * PB_BLOCK) >> 5;
+  const int64_t ncols = nb * nblk;
+  for (int64_t col = warp0; col < ncols; col += nwarps) {
+    const int64_t k = col / nb, j = col - k * nb;
+    const T* __restrict__ a = A + k * blk_stride + j * lda;
+    const T* __restrict__ rk = r + k * mb;
+    T acc = T(0);
+    int64_t i = lane;
+    for (; i + 3 * 32 < mb; i += 4 * 32) {
+      const T a0 = __ldg(a + i), a1 = __ldg(a + i + 32), a2 = __ldg(a + i + 64), a3 = __ldg(a + i + 96);
+      const T r0 = __ldg(rk + i), r1 = __ldg(rk + i + 32), r2 = __ldg(rk + i + 64), r3 = __ldg(rk + i + 96);
+      acc = fma(a0, r0, acc);
+      acc = fma(a1, r1, acc);
+      acc = fma(a2, r2, acc);
+      acc = fma(a3, r3, acc);
+    }
+    for (; i < mb; i += 32) acc = fma(__ldg(a + i), __ldg(rk + i), acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) grad[col] = acc;
+  }
+}
+
+// SquaredDistance: grad = x - b, AUX = ||x - b||^2  -> k_ew OP_SUB lives in step_kernels.cu (pb_sub); thin alias here.
+extern "C" int pb_sqdist(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* b, void* grad) {
+  return pb_sub(ctx, dtype, n, x, b, grad);
+}
+
+template <typename T>
+static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T* A, int64_t lda, int64_t blk_stride,
+                      const T* x, const T* b, T* r) {
+  const int64_t M = nblk * mb;
+  if (M == 0) {
+    // empty product: AUX = 0
+    return pb_nrm2sq(ctx, sizeof(T) == 4 ? PB_F32 : PB_F64, 0, nullptr);
+  }
+  const int64_t row_tiles = (mb + GEMV_ROWS - 1) / GEMV_ROWS;
+  // enough CTAs to cover the machine ~4x, but at least GEMV_CL*GEMV_UNROLL columns per chunk
+  int64_t target = (int64_t)ctx->sm_count * 4;
+  int64_t nchunk = target / (row_tiles * nblk);
+  if (nchunk < 1) nchunk = 1;
+  int64_t min_cols = GEMV_CL * GEMV_UNROLL;
+  if (nchunk > (nb + min_cols - 1) / min_cols) nchunk = (nb + min_cols - 1) / min_cols;
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 65535) nchunk = 65535;
+  int64_t chunk_cols = (nb + nchunk - 1) / nchunk;
+  if (chunk_cols < 1) chunk_cols = 1;
+  nchunk = nb > 0 ? (nb + chunk_cols - 1) / chunk_cols : 1;
+  PB_REQUIRE(nblk <= 65535, "too many blocks for one launch (nblk <= 65535)");
+  int rc = pb_ensure_scratch(ctx, (size_t)nchunk * M * sizeof(T));
+  if (rc != PB_OK) return rc;
+  T* partial = static_cast<T*>(ctx->scratch);
+  dim3 grid((unsigned)row_tiles, (unsigned)nchunk, (unsigned)nblk);
+  k_gemv_n_partial<T><<<grid, GEMV_ROWS * GEMV_CL, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk,
+                                                                    chunk_cols);
+  PB_LAUNCH_CHECK(ctx);
+  const int cgrid = pb_stream_grid(ctx, PB_BLOCK, M, 2);
+  k_gemv_n_combine<T><<<cgrid, PB_BLOCK, 0, ctx->stream>>>(partial, (int)nchunk, M, b, r, ctx->ws, ctx->scalars_dev);
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}
+
+template <typename T>
+static int gradient_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T* A, int64_t lda, int64_t blk_stride,
+                      const T* r, T* grad) {
+  const int64_t ncols = nblk * nb;
+  if (ncols == 0) return PB_OK;
+  const int grid = pb_stream_grid(ctx, PB_BLOCK / 32, ncols, 8);
+  k_gemv_t<T><<<grid, PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, r, grad, mb, nb, nblk);
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}
+
+static int check_common(pb_ctx* ctx, int dtype) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  return PB_OK;
+}
+
+extern "C" int pb_lsq_dense_residual(pb_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
+                                     const void* x, const void* b, void* r) {
+  int rc = check_common(ctx, dtype);
+  if (rc) return rc;
+  PB_REQUIRE(m >= 0 && n >= 0 && lda >= m, "bad shape (need m, n >= 0 and lda >= m)");
+  PB_REQUIRE(m == 0 || r != nullptr, "null output");
+  PB_REQUIRE(m == 0 || n == 0 || (A && x), "null input");
+  if (dtype == PB_F32)
+    return residual_t<float>(ctx, 1, m, n, (const float*)A, lda, 0, (const float*)x, (const float*)b, (float*)r);
+  return residual_t<double>(ctx, 1, m, n, (const double*)A, lda, 0, (const double*)x, (const double*)b, (double*)r);
+}
+
+extern "C" int pb_lsq_dense_gradient(pb_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, int64_t lda,
+                                     const void* r, void* grad) {
+  int rc = check_common(ctx, dtype);
+  if (rc) return rc;
+  PB_REQUIRE(m >= 0 && n >= 0 && lda >= m, "bad shape (need m, n >= 0 and lda >= m)");
+  PB_REQUIRE(n == 0 || grad != nullptr, "null output");
+  PB_REQUIRE(m == 0 || n == 0 || (A && r), "null input");
+  if (dtype == PB_F32) return gradient_t<float>(ctx, 1, m, n, (const float*)A, lda, 0, (const float*)r, (float*)grad);
+  return gradient_t<double>(ctx, 1, m, n, (const double*)A, lda, 0, (const double*)r, (double*)grad);
+}
+
+extern "C" int pb_lsq_blockdiag_residual(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, int64_t nb, const void* A,
+                                         const void* x, const void* b, void* r) {
+  int rc = check_common(ctx, dtype);
+  if (rc) return rc;
+  PB_REQUIRE(nblk >= 0 && mb >= 0 && nb >= 0, "bad shape");
+  PB_REQUIRE(nblk * mb == 0 || r != nullptr, "null output");
+  PB_REQUIRE(nblk * mb * nb == 0 || (A && x), "null input");
+  if (dtype == PB_F32)
+    return residual_t<float>(ctx, nblk, mb, nb, (const float*)A, mb, mb * nb, (const float*)x, (const float*)b, (float*)r);
+  return residual_t<double>(ctx, nblk, mb, nb, (const double*)A, mb, mb * nb, (const double*)x, (const double*)b,
+                            (double*)r);
+}
+
+extern "C" int pb_lsq_blockdiag_gradient(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, int64_t nb, const void* A,
+                                         const void* r, void* grad) {
+  int rc = check_common(ctx, dtype);
+  if (rc) return rc;
+  PB_REQUIRE(nblk >= 0 && mb >= 0 && nb >= 0, "bad shape");
+  PB_REQUIRE(nblk * nb == 0 || grad != nullptr, "null output");
+  PB_REQUIRE(nblk * mb * nb == 0 || (A && r), "null input");
+  if (dtype == PB_F32)
+    return gradient_t<float>(ctx, nblk, mb, nb, (const float*)A, mb, mb * nb, (const float*)r, (float*)grad);
+  return gradient_t<double>(ctx, nblk, mb, nb, (const double*)A, mb, mb * nb, (const double*)r, (double*)grad);
+}

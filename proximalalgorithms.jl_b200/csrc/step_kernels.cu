@@ -1,0 +1,682 @@
+// step_kernels.cu -- K1/K2 fused forward-backward step, K3 standalone prox, K6 vector utilities.
+//
+// Every kernel is a single coalesced HBM pass: 16-byte packed loads (float4 / double2), UNROLL independent packs per
+// input array in flight per thread, grid sized as a multiple of the SM count, per-thread double(-double) accumulators,
+// warp-shuffle -> shared -> last-CTA reduction (common.cuh).  All of them are bandwidth bound (1-3 flop/byte), so no
+// tensor-core path exists for this file.
+#include "common.cuh"
+
+// ----------------------------------------------------------------------------------------------------------------
+// element-wise prox (ProximalOperators.jl semantics, restated from the package's published algorithm)
+// ----------------------------------------------------------------------------------------------------------------
+template <typename T, int PROX>
+__device__ __forceinline__ T prox_elem(T y, T a, T b) {
+  if constexpr (PROX == PB_PROX_L1) {
+    // z = y + (y <= -gl ? gl : (y >= gl ? -gl : -y)),  a = gl = gamma*lambda
+    T sel = (y <= -a) ? a : ((y >= a) ? -a : -y);
+    return add_rn(y, sel);
+  } else if constexpr (PROX == PB_PROX_BOX) {
+    return (y < a) ? a : ((y > b) ? b : y);
+  } else if constexpr (PROX == PB_PROX_SCALE) {
+    return (a > T(1)) ? y : mul_rn(a, y);
+  } else {
+    return y;
+  }
+}
+
+struct StepParams {
+  const void* x;
+  const void* grad;
+  const void* z_prev;
+  void* y;
+  void* z;
+  void* res;
+  void* x_next;
+  const void* lo_v;
+  const void* hi_v;
+  int64_t n;
+  double gamma, beta, a, b;  // a, b: prox parameters already combined on the host in the element type
+  PbWorkspace* ws;
+  double* out;
+};
+
+template <typename T, int PROX, bool EXTRAP>
+struct StepElem {
+  // processes one element, updates accumulators; returns z and (optionally) writes y, res, x_next through references
+  template <bool COMP>
+  static __device__ __forceinline__ void run(T x, T g, T zp, T lo, T hi, T gamma, T beta, T& y, T& z, T& r, T& xn,
+                                             Acc<3, 1>& acc) {
+    y = sub_rn(x, mul_rn(gamma, g));
+    z = prox_elem<T, PROX>(y, lo, hi);
+    r = sub_rn(x, z);
+    if constexpr (EXTRAP) xn = add_rn(z, mul_rn(beta, sub_rn(z, zp)));
+    const double rd = (double)r, gd = (double)g;
+    if constexpr (COMP) {
+      if constexpr (PROX == PB_PROX_L1) dd_add(acc.s[0], fabs((double)z));
+      dd_add_prod(acc.s[1], rd, rd);
+      dd_add_prod(acc.s[2], gd, rd);
+    } else {
+      // float data: the products are exact in double; plain double accumulation per thread, double-double across threads
+      if constexpr (PROX == PB_PROX_L1) acc.s[0].hi += fabs((double)z);
+      acc.s[1].hi = __fma_rn(rd, rd, acc.s[1].hi);
+      acc.s[2].hi = __fma_rn(gd, rd, acc.s[2].hi);
+    }
+    acc.m[0] = nanmax(acc.m[0], fabs(rd));
+  }
+};
+
+template <typename T, int PROX, bool EXTRAP, int VEC, int UNROLL, bool HINT>
+__global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
+  constexpr bool COMP = sizeof(T) == 8;
+  constexpr int64_t TILE = (int64_t)PB_BLOCK * VEC * UNROLL;
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const T* __restrict__ g = static_cast<const T*>(p.grad);
+  const T* __restrict__ zp = static_cast<const T*>(p.z_prev);
+  const T* __restrict__ lov = static_cast<const T*>(p.lo_v);
+  const T* __restrict__ hiv = static_cast<const T*>(p.hi_v);
+  T* __restrict__ yo = static_cast<T*>(p.y);
+  T* __restrict__ zo = static_cast<T*>(p.z);
+  T* __restrict__ ro = static_cast<T*>(p.res);
+  T* __restrict__ xo = static_cast<T*>(p.x_next);
+  const T gamma = (T)p.gamma, beta = (T)p.beta;
+  const T pa = (T)p.a, pb = (T)p.b;
+  const int64_t n = p.n;
+  const int64_t ntiles = n / TILE;
+
+  Acc<3, 1> acc;
+  acc.clear();
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TILE + (int64_t)threadIdx.x * VEC;
+    Pack<T, VEC> xv[UNROLL], gv[UNROLL], zv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = base + (int64_t)u * PB_BLOCK * VEC;
+      xv[u] = ld_pack<T, VEC, HINT>(x + i);
+      gv[u] = ld_pack<T, VEC, HINT>(g + i);
+      if constexpr (EXTRAP) zv[u] = ld_pack<T, VEC, HINT>(zp + i);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = base + (int64_t)u * PB_BLOCK * VEC;
+      Pack<T, VEC> lo, hi, yv, zn, rv, xn;
+      if (PROX == PB_PROX_BOX && lov) lo = ld_pack<T, VEC, false>(lov + i);
+      if (PROX == PB_PROX_BOX && hiv) hi = ld_pack<T, VEC, false>(hiv + i);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const T l = (PROX == PB_PROX_BOX && lov) ? lo.v[e] : pa;
+        const T h = (PROX == PB_PROX_BOX && hiv) ? hi.v[e] : pb;
+        StepElem<T, PROX, EXTRAP>::template run<COMP>(xv[u].v[e], gv[u].v[e], EXTRAP ? zv[u].v[e] : T(0), l, h, gamma,
+                                                      beta, yv.v[e], zn.v[e], rv.v[e], xn.v[e], acc);
+      }
+      st_pack<T, VEC, HINT>(zo + i, zn);
+      if constexpr (EXTRAP) st_pack<T, VEC, HINT>(xo + i, xn);
+      if (yo) st_pack<T, VEC, HINT>(yo + i, yv);
+      if (ro) st_pack<T, VEC, HINT>(ro + i, rv);
+    }
+  }
+  // ragged tail (< TILE elements), element-wise
+  for (int64_t i = ntiles * TILE + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * PB_BLOCK) {
+    const T l = (PROX == PB_PROX_BOX && lov) ? lov[i] : pa;
+    const T h = (PROX == PB_PROX_BOX && hiv) ? hiv[i] : pb;
+    T yv, zn, rv, xn;
+    StepElem<T, PROX, EXTRAP>::template run<COMP>(x[i], g[i], EXTRAP ? zp[i] : T(0), l, h, gamma, beta, yv, zn, rv, xn,
+                                                  acc);
+    zo[i] = zn;
+    if constexpr (EXTRAP) xo[i] = xn;
+    if (yo) yo[i] = yv;
+    if (ro) ro[i] = rv;
+  }
+
+  OutMap map;
+  map.sum_slot[0] = PB_S_GSUM;
+  map.sum_slot[1] = PB_S_RESSQ;
+  map.sum_slot[2] = PB_S_GDR;
+  map.sum_slot[3] = -1;
+  map.max_slot[0] = PB_S_RESINF;
+  map.max_slot[1] = -1;
+  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// NormL21 step: one warp per contiguous group.  y is recomputed in the second sweep (group data is L1 resident).
+// group norm: float data -> exact double sum of squares; double data -> double-double.
+// ----------------------------------------------------------------------------------------------------------------
+template <typename T, bool EXTRAP>
+__global__ void __launch_bounds__(PB_BLOCK) k_step_l21(StepParams p, int group) {
+  constexpr bool COMP = sizeof(T) == 8;
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const T* __restrict__ g = static_cast<const T*>(p.grad);
+  const T* __restrict__ zp = static_cast<const T*>(p.z_prev);
+  T* __restrict__ yo = static_cast<T*>(p.y);
+  T* __restrict__ zo = static_cast<T*>(p.z);
+  T* __restrict__ ro = static_cast<T*>(p.res);
+  T* __restrict__ xo = static_cast<T*>(p.x_next);
+  const T gamma = (T)p.gamma, beta = (T)p.beta, gl = (T)p.a;
+  const int lane = threadIdx.x & 31;
+  const int64_t ngroups = p.n / group;
+  const int64_t warp0 = ((int64_t)blockIdx.x * PB_BLOCK + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * PB_BLOCK) >> 5;
+
+  Acc<3, 1> acc;
+  acc.clear();
+  for (int64_t gi = warp0; gi < ngroups; gi += nwarps) {
+    const int64_t base = gi * group;
+    dd ss;
+    ss.hi = ss.lo = 0.0;
+    for (int e = lane; e < group; e += 32) {
+      const T yv = sub_rn(x[base + e], mul_rn(gamma, g[base + e]));
+      if (COMP)
+        dd_add_prod(ss, (double)yv, (double)yv);
+      else
+        ss.hi = __fma_rn((double)yv, (double)yv, ss.hi);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      dd o;
+      o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
+      o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
+      ss = dd_sum(ss, o);
+    }
+    // nslice = sqrt(sum) in the element type; scal = 1 - gl/nslice, clamped at 0 (NaN propagates like the package)
+    const T ns = (T)sqrt(ss.hi + ss.lo);
+    T scal = sub_rn(T(1), gl / ns);
+    scal = (scal <= T(0)) ? T(0) : scal;
+    if (lane == 0) {
+      const double contrib = (double)mul_rn(scal, ns);
+      if (COMP)
+        dd_add(acc.s[0], contrib);
+      else
+        acc.s[0].hi += contrib;
+    }
+    for (int e = lane; e < group; e += 32) {
+      const T xv = x[base + e], gv = g[base + e];
+      const T yv = sub_rn(xv, mul_rn(gamma, gv));
+      const T zv = mul_rn(scal, yv);
+      const T rv = sub_rn(xv, zv);
+      zo[base + e] = zv;
+      if (yo) yo[base + e] = yv;
+      if (ro) ro[base + e] = rv;
+      if constexpr (EXTRAP) xo[base + e] = add_rn(zv, mul_rn(beta, sub_rn(zv, zp[base + e])));
+      const double rd = (double)rv, gd = (double)gv;
+      if (COMP) {
+        dd_add_prod(acc.s[1], rd, rd);
+        dd_add_prod(acc.s[2], gd, rd);
+      } else {
+        acc.s[1].hi = __fma_rn(rd, rd, acc.s[1].hi);
+        acc.s[2].hi = __fma_rn(gd, rd, acc.s[2].hi);
+      }
+      acc.m[0] = nanmax(acc.m[0], fabs(rd));
+    }
+  }
+  OutMap map;
+  map.sum_slot[0] = PB_S_GSUM;
+  map.sum_slot[1] = PB_S_RESSQ;
+  map.sum_slot[2] = PB_S_GDR;
+  map.sum_slot[3] = -1;
+  map.max_slot[0] = PB_S_RESINF;
+  map.max_slot[1] = -1;
+  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// generic element-wise kernel with up to three inputs, one output and one sum / one max reduction (K3, K6)
+// ----------------------------------------------------------------------------------------------------------------
+enum {
+  OP_PROX_L1 = 0,   // out = prox_l1(a; gl = s0);                    sum = |out|
+  OP_PROX_BOX,      // out = clamp(a, s0 | b[], s1 | c[]);
+  OP_PROX_SCALE,    // out = s0 > 1 ? a : s0*a
+  OP_COPY,          // out = a
+  OP_FORWARD,       // out = a - s0*b;                                 sum = out^2
+  OP_EXTRAP,        // out = a + s0*(a - b)
+  OP_RESIDUAL,      // out = a - b;   sums: (a-b)^2, c*(a-b) (c optional), max |a-b|  -> handled by k_residual
+  OP_ADD_SCALAR,    // out = a + s0
+  OP_SUB,           // out = a - b;                                    sum = out^2
+  OP_NRM2SQ,        // (no out)                                        sum = a^2,  max = |a|
+  OP_DOT            // (no out)                                        sum = a*b
+};
+
+struct EwParams {
+  const void* a;
+  const void* b;
+  const void* c;
+  void* out;
+  int64_t n;
+  double s0, s1;
+  PbWorkspace* ws;
+  double* outs;
+  int sum_slot, max_slot;
+};
+
+template <typename T, int OP, bool COMP>
+__device__ __forceinline__ T ew_elem(T a, T b, T c, T s0, T s1, bool hb, bool hc, Acc<1, 1>& acc) {
+  T o = a;
+  double sum_term = 0.0;
+  bool have_sum = false, have_prod = false;
+  double pa = 0.0, pb = 0.0;
+  if constexpr (OP == OP_PROX_L1) {
+    o = prox_elem<T, PB_PROX_L1>(a, s0, s1);
+    sum_term = fabs((double)o);
+    have_sum = true;
+  } else if constexpr (OP == OP_PROX_BOX) {
+    o = prox_elem<T, PB_PROX_BOX>(a, hb ? b : s0, hc ? c : s1);
+  } else if constexpr (OP == OP_PROX_SCALE) {
+    o = prox_elem<T, PB_PROX_SCALE>(a, s0, s1);
+  } else if constexpr (OP == OP_FORWARD) {
+    o = sub_rn(a, mul_rn(s0, b));
+    pa = pb = (double)o;
+    have_prod = true;
+  } else if constexpr (OP == OP_EXTRAP) {
+    o = add_rn(a, mul_rn(s0, sub_rn(a, b)));
+  } else if constexpr (OP == OP_ADD_SCALAR) {
+    o = add_rn(a, s0);
+  } else if constexpr (OP == OP_SUB) {
+    o = sub_rn(a, b);
+    pa = pb = (double)o;
+    have_prod = true;
+  } else if constexpr (OP == OP_NRM2SQ) {
+    pa = pb = (double)a;
+    have_prod = true;
+    acc.m[0] = nanmax(acc.m[0], fabs((double)a));
+  } else if constexpr (OP == OP_DOT) {
+    pa = (double)a;
+    pb = (double)b;
+    have_prod = true;
+  }
+  if (have_sum) {
+    if (COMP)
+      dd_add(acc.s[0], sum_term);
+    else
+      acc.s[0].hi += sum_term;
+  }
+  if (have_prod) {
+    if (COMP)
+      dd_add_prod(acc.s[0], pa, pb);
+    else
+      acc.s[0].hi = __fma_rn(pa, pb, acc.s[0].hi);
+  }
+  return o;
+}
+
+template <typename T, int OP, int VEC, int UNROLL>
+__global__ void __launch_bounds__(PB_BLOCK) k_ew(EwParams p) {
+  constexpr bool COMP = sizeof(T) == 8;
+  constexpr bool USES_B = (OP == OP_FORWARD || OP == OP_EXTRAP || OP == OP_SUB || OP == OP_DOT);
+  constexpr bool HAS_OUT = !(OP == OP_NRM2SQ || OP == OP_DOT);
+  constexpr int64_t TILE = (int64_t)PB_BLOCK * VEC * UNROLL;
+  const T* __restrict__ a = static_cast<const T*>(p.a);
+  const T* __restrict__ b = static_cast<const T*>(p.b);
+  const T* __restrict__ c = static_cast<const T*>(p.c);
+  T* __restrict__ out = static_cast<T*>(p.out);
+  const bool hb = (OP == OP_PROX_BOX) && b != nullptr;
+  const bool hc = (OP == OP_PROX_BOX) && c != nullptr;
+  const T s0 = (T)p.s0, s1 = (T)p.s1;
+  const int64_t n = p.n, ntiles = n / TILE;
+  Acc<1, 1> acc;
+  acc.clear();
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * TILE + (int64_t)threadIdx.x * VEC;
+    Pack<T, VEC> av[UNROLL], bv[UNROLL], cv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = base + (int64_t)u * PB_BLOCK * VEC;
+      av[u] = ld_pack<T, VEC, false>(a + i);
+      if (USES_B || hb) bv[u] = ld_pack<T, VEC, false>(b + i);
+      if (hc) cv[u] = ld_pack<T, VEC, false>(c + i);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = base + (int64_t)u * PB_BLOCK * VEC;
+      Pack<T, VEC> o;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        o.v[e] = ew_elem<T, OP, COMP>(av[u].v[e], (USES_B || hb) ? bv[u].v[e] : T(0), hc ? cv[u].v[e] : T(0), s0, s1, hb,
+                                      hc, acc);
+      if constexpr (HAS_OUT) st_pack<T, VEC, false>(out + i, o);
+    }
+  }
+  for (int64_t i = ntiles * TILE + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * PB_BLOCK) {
+    const T o = ew_elem<T, OP, COMP>(a[i], (USES_B || hb) ? b[i] : T(0), hc ? c[i] : T(0), s0, s1, hb, hc, acc);
+    if constexpr (HAS_OUT) out[i] = o;
+  }
+  if (p.sum_slot >= 0 || p.max_slot >= 0) {
+    OutMap map;
+    map.sum_slot[0] = p.sum_slot;
+    map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
+    map.max_slot[0] = p.max_slot;
+    map.max_slot[1] = -1;
+    grid_reduce<1, 1, PB_BLOCK>(acc, p.ws, p.outs, map);
+  }
+}
+
+// res = x - z with RESSQ, RESINF and optionally GDR
+template <typename T>
+__global__ void __launch_bounds__(PB_BLOCK) k_residual(const T* __restrict__ x, const T* __restrict__ z,
+                                                       const T* __restrict__ g, T* __restrict__ res, int64_t n,
+                                                       PbWorkspace* ws, double* outs) {
+  constexpr bool COMP = sizeof(T) == 8;
+  Acc<2, 1> acc;
+  acc.clear();
+  for (int64_t i = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * PB_BLOCK) {
+    const T r = sub_rn(x[i], z[i]);
+    if (res) res[i] = r;
+    const double rd = (double)r;
+    if (COMP) {
+      dd_add_prod(acc.s[0], rd, rd);
+      if (g) dd_add_prod(acc.s[1], (double)g[i], rd);
+    } else {
+      acc.s[0].hi = __fma_rn(rd, rd, acc.s[0].hi);
+      if (g) acc.s[1].hi = __fma_rn((double)g[i], rd, acc.s[1].hi);
+    }
+    acc.m[0] = nanmax(acc.m[0], fabs(rd));
+  }
+  OutMap map;
+  map.sum_slot[0] = PB_S_RESSQ;
+  map.sum_slot[1] = g ? PB_S_GDR : -1;
+  map.sum_slot[2] = map.sum_slot[3] = -1;
+  map.max_slot[0] = PB_S_RESINF;
+  map.max_slot[1] = -1;
+  grid_reduce<2, 1, PB_BLOCK>(acc, ws, outs, map);
+}
+
+// NormL21 standalone prox, one warp per group
+template <typename T>
+__global__ void __launch_bounds__(PB_BLOCK) k_prox_l21(const T* __restrict__ y, T* __restrict__ z, int64_t n, int group,
+                                                       double gl_d, PbWorkspace* ws, double* outs) {
+  constexpr bool COMP = sizeof(T) == 8;
+  const T gl = (T)gl_d;
+  const int lane = threadIdx.x & 31;
+  const int64_t ngroups = n / group;
+  const int64_t warp0 = ((int64_t)blockIdx.x * PB_BLOCK + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * PB_BLOCK) >> 5;
+  Acc<1, 1> acc;
+  acc.clear();
+  for (int64_t gi = warp0; gi < ngroups; gi += nwarps) {
+    const int64_t base = gi * group;
+    dd ss;
+    ss.hi = ss.lo = 0.0;
+    for (int e = lane; e < group; e += 32) {
+      const double yv = (double)y[base + e];
+      if (COMP)
+        dd_add_prod(ss, yv, yv);
+      else
+        ss.hi = __fma_rn(yv, yv, ss.hi);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      dd o;
+      o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
+      o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
+      ss = dd_sum(ss, o);
+    }
+    const T ns = (T)sqrt(ss.hi + ss.lo);
+    T scal = sub_rn(T(1), gl / ns);
+    scal = (scal <= T(0)) ? T(0) : scal;
+    if (lane == 0) {
+      const double contrib = (double)mul_rn(scal, ns);
+      if (COMP)
+        dd_add(acc.s[0], contrib);
+      else
+        acc.s[0].hi += contrib;
+    }
+    for (int e = lane; e < group; e += 32) z[base + e] = mul_rn(scal, y[base + e]);
+  }
+  OutMap map;
+  map.sum_slot[0] = PB_S_GSUM;
+  map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
+  map.max_slot[0] = map.max_slot[1] = -1;
+  grid_reduce<1, 1, PB_BLOCK>(acc, ws, outs, map);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ----------------------------------------------------------------------------------------------------------------
+static bool use_hints(const pb_ctx* ctx, int64_t n, size_t elt, int nvec) {
+  if (ctx->stream_hints >= 0) return ctx->stream_hints != 0;
+  return (size_t)n * elt * nvec > ctx->l2_bytes;  // working set cannot live in L2: stream through it
+}
+
+template <typename T, int PROX, bool EXTRAP>
+static int launch_step_t(pb_ctx* ctx, const StepParams& p, bool vec_ok) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int UNROLL = 4;
+  const bool hint = use_hints(ctx, p.n, sizeof(T), EXTRAP ? 5 : 3);
+  if (vec_ok) {
+    const int grid = pb_stream_grid(ctx, (int64_t)PB_BLOCK * VEC * UNROLL, p.n, 4);
+    if (hint)
+      k_step<T, PROX, EXTRAP, VEC, UNROLL, true><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+    else
+      k_step<T, PROX, EXTRAP, VEC, UNROLL, false><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+  } else {
+    const int grid = pb_stream_grid(ctx, (int64_t)PB_BLOCK * UNROLL, p.n, 4);
+    k_step<T, PROX, EXTRAP, 1, UNROLL, false><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+  }
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}
+
+template <typename T, bool EXTRAP>
+static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool vec_ok) {
+  const T gamma = (T)p.gamma;
+  switch (g->kind) {
+    case PB_PROX_ZERO:
+      return launch_step_t<T, PB_PROX_ZERO, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_L1:
+      p.a = (double)mul_rn_host(gamma, (T)g->p0);
+      return launch_step_t<T, PB_PROX_L1, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_BOX:
+      p.a = g->p0;
+      p.b = g->p1;
+      p.lo_v = g->v0;
+      p.hi_v = g->v1;
+      if ((p.lo_v && !pb_aligned16(p.lo_v)) || (p.hi_v && !pb_aligned16(p.hi_v))) vec_ok = false;
+      return launch_step_t<T, PB_PROX_BOX, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_SCALE:
+      p.a = g->p0;
+      return launch_step_t<T, PB_PROX_SCALE, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_L21: {
+      PB_REQUIRE(g->group > 0 && p.n % g->group == 0, "NormL21 group must divide n");
+      p.a = (double)mul_rn_host(gamma, (T)g->p0);
+      const int64_t ngroups = p.n / g->group;
+      const int grid = pb_stream_grid(ctx, PB_BLOCK / 32, ngroups, 8);
+      k_step_l21<T, EXTRAP><<<grid, PB_BLOCK, 0, ctx->stream>>>(p, g->group);
+      PB_LAUNCH_CHECK(ctx);
+      return PB_OK;
+    }
+    default:
+      pb_set_error("unknown prox kind %d", g->kind);
+      return PB_EINVAL;
+  }
+}
+
+static int step_common(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev,
+                       double gamma, double beta, const pb_prox* g, void* y, void* z, void* res, void* x_next,
+                       bool extrap) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  PB_REQUIRE(n >= 0, "negative length");
+  PB_REQUIRE(g != nullptr, "null prox descriptor");
+  PB_REQUIRE(n == 0 || (x && grad && z), "null vector");
+  PB_REQUIRE(!extrap || n == 0 || (z_prev && x_next), "null z_prev / x_next");
+  PB_REQUIRE(!extrap || x_next != x, "x_next must not alias x");
+  StepParams p;
+  p.x = x;
+  p.grad = grad;
+  p.z_prev = z_prev;
+  p.y = y;
+  p.z = z;
+  p.res = res;
+  p.x_next = x_next;
+  p.lo_v = p.hi_v = nullptr;
+  p.n = n;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.a = p.b = 0.0;
+  p.ws = ctx->ws;
+  p.out = ctx->scalars_dev;
+  bool vec_ok = pb_aligned16(x) && pb_aligned16(grad) && pb_aligned16(z) && (!y || pb_aligned16(y)) &&
+                (!res || pb_aligned16(res)) && (!extrap || (pb_aligned16(z_prev) && pb_aligned16(x_next)));
+  if (dtype == PB_F32)
+    return extrap ? launch_step_prox<float, true>(ctx, p, g, vec_ok) : launch_step_prox<float, false>(ctx, p, g, vec_ok);
+  return extrap ? launch_step_prox<double, true>(ctx, p, g, vec_ok) : launch_step_prox<double, false>(ctx, p, g, vec_ok);
+}
+
+extern "C" int pb_fb_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, double gamma,
+                          const pb_prox* g, void* y, void* z, void* res) {
+  return step_common(ctx, dtype, n, x, grad, nullptr, gamma, 0.0, g, y, z, res, nullptr, false);
+}
+
+extern "C" int pb_ffb_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev,
+                           double gamma, double beta, const pb_prox* g, void* y, void* z, void* res, void* x_next) {
+  return step_common(ctx, dtype, n, x, grad, z_prev, gamma, beta, g, y, z, res, x_next, true);
+}
+
+// ---- element-wise utilities ------------------------------------------------------------------------------------
+template <typename T, int OP>
+static int launch_ew_t(pb_ctx* ctx, const EwParams& p) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int UNROLL = 4;
+  const bool vec_ok = pb_aligned16(p.a) && (!p.b || pb_aligned16(p.b)) && (!p.c || pb_aligned16(p.c)) &&
+                      (!p.out || pb_aligned16(p.out));
+  if (vec_ok) {
+    const int grid = pb_stream_grid(ctx, (int64_t)PB_BLOCK * VEC * UNROLL, p.n, 4);
+    k_ew<T, OP, VEC, UNROLL><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+  } else {
+    const int grid = pb_stream_grid(ctx, (int64_t)PB_BLOCK * UNROLL, p.n, 4);
+    k_ew<T, OP, 1, UNROLL><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+  }
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}
+
+template <int OP>
+static int launch_ew(pb_ctx* ctx, int dtype, int64_t n, const void* a, const void* b, const void* c, void* out,
+                     double s0, double s1, int sum_slot, int max_slot) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  PB_REQUIRE(n >= 0, "negative length");
+  PB_REQUIRE(n == 0 || a != nullptr, "null vector");
+  EwParams p;
+  p.a = a;
+  p.b = b;
+  p.c = c;
+  p.out = out;
+  p.n = n;
+  p.s0 = s0;
+  p.s1 = s1;
+  p.ws = ctx->ws;
+  p.outs = ctx->scalars_dev;
+  p.sum_slot = sum_slot;
+  p.max_slot = max_slot;
+  return dtype == PB_F32 ? launch_ew_t<float, OP>(ctx, p) : launch_ew_t<double, OP>(ctx, p);
+}
+
+extern "C" int pb_prox_apply(pb_ctx* ctx, int dtype, int64_t n, const void* y, double gamma, const pb_prox* g, void* z) {
+  PB_REQUIRE(g != nullptr, "null prox descriptor");
+  PB_REQUIRE(n == 0 || z != nullptr, "null output");
+  switch (g->kind) {
+    case PB_PROX_ZERO:
+      return launch_ew<OP_COPY>(ctx, dtype, n, y, nullptr, nullptr, z, 0, 0, -1, -1);
+    case PB_PROX_L1: {
+      const double gl = dtype == PB_F32 ? (double)mul_rn_host((float)gamma, (float)g->p0) : mul_rn_host(gamma, g->p0);
+      return launch_ew<OP_PROX_L1>(ctx, dtype, n, y, nullptr, nullptr, z, gl, 0, PB_S_GSUM, -1);
+    }
+    case PB_PROX_BOX:
+      return launch_ew<OP_PROX_BOX>(ctx, dtype, n, y, g->v0, g->v1, z, g->p0, g->p1, -1, -1);
+    case PB_PROX_SCALE:
+      return launch_ew<OP_PROX_SCALE>(ctx, dtype, n, y, nullptr, nullptr, z, g->p0, 0, -1, -1);
+    case PB_PROX_L21: {
+      PB_REQUIRE(ctx != nullptr, "null context");
+      PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+      PB_REQUIRE(g->group > 0 && n % g->group == 0, "NormL21 group must divide n");
+      const int grid = pb_stream_grid(ctx, PB_BLOCK / 32, n / g->group, 8);
+      if (dtype == PB_F32)
+        k_prox_l21<float><<<grid, PB_BLOCK, 0, ctx->stream>>>((const float*)y, (float*)z, n, g->group,
+                                                               (double)mul_rn_host((float)gamma, (float)g->p0), ctx->ws,
+                                                               ctx->scalars_dev);
+      else
+        k_prox_l21<double><<<grid, PB_BLOCK, 0, ctx->stream>>>((const double*)y, (double*)z, n, g->group,
+                                                                mul_rn_host(gamma, g->p0), ctx->ws, ctx->scalars_dev);
+      PB_LAUNCH_CHECK(ctx);
+      return PB_OK;
+    }
+    default:
+      pb_set_error("unknown prox kind %d", g->kind);
+      return PB_EINVAL;
+  }
+}
+
+extern "C" int pb_forward(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, double gamma, void* y) {
+  PB_REQUIRE(n == 0 || (grad && y), "null vector");
+  return launch_ew<OP_FORWARD>(ctx, dtype, n, x, grad, nullptr, y, gamma, 0, PB_S_AUX, -1);
+}
+
+extern "C" int pb_extrapolate(pb_ctx* ctx, int dtype, int64_t n, const void* z, const void* z_prev, double beta, void* x) {
+  PB_REQUIRE(n == 0 || (z_prev && x), "null vector");
+  return launch_ew<OP_EXTRAP>(ctx, dtype, n, z, z_prev, nullptr, x, beta, 0, -1, -1);
+}
+
+extern "C" int pb_add_scalar(pb_ctx* ctx, int dtype, int64_t n, const void* x, double c, void* out) {
+  PB_REQUIRE(n == 0 || out, "null vector");
+  return launch_ew<OP_ADD_SCALAR>(ctx, dtype, n, x, nullptr, nullptr, out, c, 0, -1, -1);
+}
+
+extern "C" int pb_sub(pb_ctx* ctx, int dtype, int64_t n, const void* a, const void* b, void* out) {
+  PB_REQUIRE(n == 0 || (b && out), "null vector");
+  return launch_ew<OP_SUB>(ctx, dtype, n, a, b, nullptr, out, 0, 0, PB_S_AUX, -1);
+}
+
+extern "C" int pb_nrm2sq(pb_ctx* ctx, int dtype, int64_t n, const void* v) {
+  return launch_ew<OP_NRM2SQ>(ctx, dtype, n, v, nullptr, nullptr, nullptr, 0, 0, PB_S_AUX, PB_S_AUXINF);
+}
+
+extern "C" int pb_dot(pb_ctx* ctx, int dtype, int64_t n, const void* a, const void* b) {
+  PB_REQUIRE(n == 0 || b, "null vector");
+  return launch_ew<OP_DOT>(ctx, dtype, n, a, b, nullptr, nullptr, 0, 0, PB_S_AUX, -1);
+}
+
+extern "C" int pb_residual(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* z, const void* grad, void* res) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  PB_REQUIRE(n >= 0, "negative length");
+  PB_REQUIRE(n == 0 || (x && z), "null vector");
+  const int grid = pb_stream_grid(ctx, PB_BLOCK * 4, n, 4);
+  if (dtype == PB_F32)
+    k_residual<float><<<grid, PB_BLOCK, 0, ctx->stream>>>((const float*)x, (const float*)z, (const float*)grad,
+                                                           (float*)res, n, ctx->ws, ctx->scalars_dev);
+  else
+    k_residual<double><<<grid, PB_BLOCK, 0, ctx->stream>>>((const double*)x, (const double*)z, (const double*)grad,
+                                                            (double*)res, n, ctx->ws, ctx->scalars_dev);
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}
+
+// ---- host-buffer entry point -------------------------------------------------------------------------------------
+extern "C" int pb_ffb_step_host(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev,
+                                double gamma, double beta, const pb_prox* g, void* z, void* x_next, double* scalars) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  PB_REQUIRE(n >= 0, "negative length");
+  PB_REQUIRE(n == 0 || (x && grad && z_prev && z && x_next), "null host vector");
+  const size_t bytes = (size_t)n * (dtype == PB_F32 ? 4 : 8);
+  if (ctx->hbuf_bytes < bytes) {
+    for (int k = 0; k < 5; ++k) {
+      if (ctx->hbuf[k]) cudaFree(ctx->hbuf[k]);
+      ctx->hbuf[k] = nullptr;
+    }
+    ctx->hbuf_bytes = 0;
+    for (int k = 0; k < 5; ++k) PB_CHECK_CUDA(cudaMalloc(&ctx->hbuf[k], bytes ? bytes : 16));
+    ctx->hbuf_bytes = bytes;
+  }
+  PB_CHECK_CUDA(cudaMemcpyAsync(ctx->hbuf[0], x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PB_CHECK_CUDA(cudaMemcpyAsync(ctx->hbuf[1], grad, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PB_CHECK_CUDA(cudaMemcpyAsync(ctx->hbuf[2], z_prev, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pb_ffb_step(ctx, dtype, n, ctx->hbuf[0], ctx->hbuf[1], ctx->hbuf[2], gamma, beta, g, nullptr, ctx->hbuf[3],
+                       nullptr, ctx->hbuf[4]);
+  if (rc != PB_OK) return rc;
+  PB_CHECK_CUDA(cudaMemcpyAsync(z, ctx->hbuf[3], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PB_CHECK_CUDA(cudaMemcpyAsync(x_next, ctx->hbuf[4], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (scalars) return pb_read_scalars(ctx, scalars);
+  PB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PB_OK;
+}

@@ -1,0 +1,342 @@
+"""First-order oracles of the hot path: smooth terms (value_and_gradient) and proximable terms (prox!).
+
+Mirrors the callback contract of the reference:
+  * `value_and_gradient(f, x) -> (f(x), grad)`   src/ProximalAlgorithms.jl:27-40, benchmark/benchmarks.jl:11-28
+  * `prox!(z, g, y, gamma) -> g(z)`              ProximalCore; call sites fast_forward_backward.jl:80,141,
+                                                  forward_backward.jl:72,118, fb_tools.jl:49
+User types plug in by duck typing: any object with `value_and_gradient(x)` is a smooth term, any object with
+`prox_(z, y, gamma)` (in place, returns g(z)) is a proximable term; both operate on 1-D CUDA tensors.  The built-in
+types below additionally expose the device fast path (kernels of libproxb200 with the value left in the scalar block).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .host import Context, LocalComm, check_vec, pb_dtype, ptr, real_type, torch
+
+
+class Deferred:
+    """A scalar whose value is still in the device scalar block; resolved after the per-iteration read-back.
+    `fn(local_row, combined)` gets this rank's raw row and the rank-combined `Scalars`."""
+
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def resolve(self, local_row, combined):
+        return self.fn(local_row, combined)
+
+
+def _sq_half(R, sum_sq):
+    """`norm(v)^2 / 2` with Julia's sqrt-then-square rounding (benchmark/benchmarks.jl:16) from an exact sum of squares."""
+    nr = R(np.sqrt(np.float64(sum_sq)))
+    return R(R(nr * nr) / R(2))
+
+
+def _as_device(a, device, dtype=None):
+    t = torch()
+    if isinstance(a, t.Tensor):
+        out = a.to(device=device, dtype=dtype if dtype is not None else a.dtype)
+    else:
+        out = t.as_tensor(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
+    return out
+
+
+# =====================================================================================================================
+# smooth terms
+# =====================================================================================================================
+
+
+class Zero:
+    """ProximalCore.Zero: f = 0 with gradient zero(x) (src/ProximalAlgorithms.jl:38-40); as g its prox is the identity."""
+
+    kind = L.PB_PROX_ZERO
+    fused = True
+
+    def value_and_gradient(self, x):
+        return real_type(x.dtype)(0), torch().zeros_like(x)
+
+    def value_and_gradient_into(self, ctx, x, grad):
+        grad.zero_()
+        return real_type(x.dtype)(0)
+
+    def descriptor(self, R):
+        return L.pb_prox(L.PB_PROX_ZERO, 0, 0.0, 0.0, None, None)
+
+    def value_from(self, R, scal):
+        return R(0)
+
+
+class LeastSquares:
+    """f(x) = 0.5*||A x - b||^2 for a dense matrix, with the benchmark's explicit gradient
+    `res = A*x - b; (norm(res)^2/2, A'*res)` (benchmark/benchmarks.jl:11-17).
+
+    A is kept column-major on the device (Julia layout).  With `comm` of size P > 1, `A` is this rank's COLUMN shard
+    (matching the row shard of x): the m-vector of partial products is all-gathered and folded in rank order
+    (SURVEY.md section 8e), then `A_p' r` is local.
+    """
+
+    def __init__(self, A, b, comm=None, device=None):
+        t = torch()
+        ctx = Context.get(device)
+        self.ctx = ctx
+        self.comm = comm or LocalComm()
+        if isinstance(A, t.Tensor):
+            R = real_type(A.dtype)
+            a_cm = A.to(ctx.device).t().contiguous()          # (n, m) row-major == A column-major
+        else:
+            A = np.asarray(A)
+            R = real_type(A.dtype)
+            a_cm = t.as_tensor(np.ascontiguousarray(A.T)).to(ctx.device)
+        self.R = R
+        self.m, self.n = int(a_cm.shape[1]), int(a_cm.shape[0])
+        self.A_cm = a_cm
+        self.b = _as_device(b, ctx.device, a_cm.dtype).contiguous()
+        check_vec(self.b, self.m, a_cm.dtype)
+        self.r = t.empty(self.m, dtype=a_cm.dtype, device=ctx.device)
+        self.calls = 0
+
+    def _residual(self, x):
+        lib, ctx, dt = self.ctx.lib, self.ctx, pb_dtype(self.R)
+        check_vec(x, self.n, self.A_cm.dtype)
+        if self.comm.size == 1:
+            L.check(lib.pb_lsq_dense_residual(ctx.h, dt, self.m, self.n, ptr(self.A_cm), self.m, ptr(x), ptr(self.b), ptr(self.r)))
+            return Deferred(lambda row, comb: _sq_half(self.R, row[L.PB_S_AUX] + row[L.PB_S_AUX + 1]))
+        # column shard: partial product, all-gather, fixed-order fold, subtract b, ||r||^2 (replicated on every rank)
+        L.check(lib.pb_lsq_dense_residual(ctx.h, dt, self.m, self.n, ptr(self.A_cm), self.m, ptr(x), None, ptr(self.r)))
+        parts = self.comm.allgather_vector(self.r)
+        acc = parts[0].clone()
+        for p in range(1, parts.shape[0]):
+            acc += parts[p]
+        L.check(lib.pb_sub(ctx.h, dt, self.m, ptr(acc), ptr(self.b), ptr(self.r)))
+        return Deferred(lambda row, comb: _sq_half(self.R, row[L.PB_S_AUX] + row[L.PB_S_AUX + 1]))
+
+    def value_and_gradient_into(self, ctx, x, grad):
+        """Device fast path: enqueue r = A x - b (AUX = ||r||^2) and grad = A' r; the value is Deferred."""
+        self.calls += 1
+        val = self._residual(x)
+        L.check(ctx.lib.pb_lsq_dense_gradient(ctx.h, pb_dtype(self.R), self.m, self.n, ptr(self.A_cm), self.m, ptr(self.r), ptr(grad)))
+        return val
+
+    def value_into(self, ctx, x):
+        """f(x) only: the reference discards the gradient of the FFB line search (fast_forward_backward.jl:112-128
+        passes grad_f_Az = nothing), so skipping A' r there is parity-safe (hard part 8 iii)."""
+        self.calls += 1
+        return self._residual(x)
+
+    def value_and_gradient(self, x):
+        """Reference-shaped allocating form."""
+        grad = torch().empty_like(x)
+        val = self.value_and_gradient_into(self.ctx, x, grad)
+        row = self.ctx.read_scalars()
+        return val.resolve(row, None), grad
+
+
+class BlockDiagLeastSquares:
+    """f(x) = 0.5*||A x - b||^2, A = blockdiag(A_1..A_B), A_k in R^{mb x nb} ("A implicit, Ax via batched GEMV",
+    BASELINE.json configs[1]; structure fixed by SURVEY.md section 7 hard part 6).  `blocks_cm` is a (B, nb, mb) tensor, i.e.
+    every block column-major.  Sharding: whole blocks per rank, no vector collective; the value is summed with the
+    scalar block."""
+
+    def __init__(self, blocks_cm, b, comm=None):
+        t = torch()
+        if not (isinstance(blocks_cm, t.Tensor) and blocks_cm.is_cuda and blocks_cm.dim() == 3 and blocks_cm.is_contiguous()):
+            raise ValueError("blocks_cm must be a contiguous (B, nb, mb) CUDA tensor (each block column-major)")
+        self.ctx = Context.get(blocks_cm.device)
+        self.comm = comm or LocalComm()
+        self.R = real_type(blocks_cm.dtype)
+        self.nblk, self.nb, self.mb = (int(s) for s in blocks_cm.shape)
+        self.A = blocks_cm
+        self.b = b
+        check_vec(b, self.nblk * self.mb, blocks_cm.dtype)
+        self.r = t.empty_like(b)
+        self.n = self.nblk * self.nb
+        self.calls = 0
+
+    @classmethod
+    def from_numpy(cls, blocks, b, device=None, comm=None):
+        """blocks: (B, mb, nb) array in the mathematical orientation."""
+        t = torch()
+        ctx = Context.get(device)
+        cm = t.as_tensor(np.ascontiguousarray(np.transpose(blocks, (0, 2, 1)))).to(ctx.device)
+        return cls(cm, t.as_tensor(np.ascontiguousarray(b)).to(ctx.device), comm=comm)
+
+    def _residual(self, ctx, x):
+        check_vec(x, self.n, self.A.dtype)
+        L.check(ctx.lib.pb_lsq_blockdiag_residual(ctx.h, pb_dtype(self.R), self.nblk, self.mb, self.nb, ptr(self.A), ptr(x), ptr(self.b), ptr(self.r)))
+        return Deferred(lambda row, comb: _sq_half(self.R, comb.aux if comb is not None else row[L.PB_S_AUX] + row[L.PB_S_AUX + 1]))
+
+    def value_and_gradient_into(self, ctx, x, grad):
+        self.calls += 1
+        val = self._residual(ctx, x)
+        L.check(ctx.lib.pb_lsq_blockdiag_gradient(ctx.h, pb_dtype(self.R), self.nblk, self.mb, self.nb, ptr(self.A), ptr(self.r), ptr(grad)))
+        return val
+
+    def value_into(self, ctx, x):
+        self.calls += 1
+        return self._residual(ctx, x)
+
+    def value_and_gradient(self, x):
+        grad = torch().empty_like(x)
+        val = self.value_and_gradient_into(self.ctx, x, grad)
+        return val.resolve(self.ctx.read_scalars(), None), grad
+
+
+class SquaredDistance:
+    """benchmark/benchmarks.jl:19-28: f(x) = norm(x - b)^2/2 with gradient x - b (one fused pass)."""
+
+    def __init__(self, b, device=None):
+        self.ctx = Context.get(device if device is not None else (b.device if hasattr(b, "is_cuda") and b.is_cuda else None))
+        self.b = _as_device(b, self.ctx.device).contiguous()
+        self.R = real_type(self.b.dtype)
+
+    def value_and_gradient_into(self, ctx, x, grad):
+        check_vec(x, self.b.numel(), self.b.dtype)
+        L.check(ctx.lib.pb_sqdist(ctx.h, pb_dtype(self.R), x.numel(), ptr(x), ptr(self.b), ptr(grad)))
+        return Deferred(lambda row, comb: _sq_half(self.R, comb.aux if comb is not None else row[L.PB_S_AUX] + row[L.PB_S_AUX + 1]))
+
+    def value_and_gradient(self, x):
+        grad = torch().empty_like(x)
+        val = self.value_and_gradient_into(self.ctx, x, grad)
+        return val.resolve(self.ctx.read_scalars(), None), grad
+
+
+class LinearFunction:
+    """f(x) = <c, x>: constant gradient c.  This is the "gradient supplied as a buffer" smooth term of the fused-step-only
+    workloads (BASELINE.json configs[2]): value_and_gradient_into leaves `grad` aliasing... no copy
+    is made when the iteration's gradient buffer IS `c` (see algorithms._eval_f)."""
+
+    def __init__(self, c):
+        self.c = c
+        self.R = real_type(c.dtype)
+        self.ctx = Context.get(c.device)
+
+    def gradient_buffer(self):
+        return self.c
+
+    def value_and_gradient_into(self, ctx, x, grad):
+        if grad.data_ptr() != self.c.data_ptr():
+            grad.copy_(self.c)
+        L.check(ctx.lib.pb_dot(ctx.h, pb_dtype(self.R), x.numel(), ptr(self.c), ptr(x)))
+        return Deferred(lambda row, comb: self.R(comb.aux if comb is not None else row[L.PB_S_AUX] + row[L.PB_S_AUX + 1]))
+
+    def value_and_gradient(self, x):
+        val = self.value_and_gradient_into(self.ctx, x, self.c)
+        return val.resolve(self.ctx.read_scalars(), None), self.c.clone()
+
+
+# =====================================================================================================================
+# proximable terms (ProximalOperators.jl 0.15 semantics; the kernels live in csrc/step_kernels.cu)
+# =====================================================================================================================
+
+
+class _FusedProx:
+    fused = True
+
+    def prox_(self, z, y, gamma):
+        """Reference-shaped in-place prox!(z, g, y, gamma) -> g(z) (standalone kernel K3)."""
+        ctx = Context.get(y.device)
+        R = real_type(y.dtype)
+        d = self.descriptor(R)
+        L.check(ctx.lib.pb_prox_apply(ctx.h, pb_dtype(R), y.numel(), ptr(y), float(gamma), C.byref(d), ptr(z)))
+        if self.kind in (L.PB_PROX_L1, L.PB_PROX_L21):
+            row = ctx.read_scalars()
+            return self.value_from(R, row[L.PB_S_GSUM] + row[L.PB_S_GSUM + 1])
+        return R(0)
+
+    def value_from(self, R, gsum):
+        return R(0)
+
+
+class NormL1(_FusedProx):
+    """g(x) = lambda*||x||_1 (benchmark/benchmarks.jl:52,60)."""
+
+    kind = L.PB_PROX_L1
+
+    def __init__(self, lam=1.0):
+        if lam < 0:
+            raise ValueError("parameter lambda must be nonnegative")
+        self.lam = lam
+
+    def descriptor(self, R):
+        return L.pb_prox(L.PB_PROX_L1, 0, float(R(self.lam)), 0.0, None, None)
+
+    def value_from(self, R, gsum):
+        return R(R(self.lam) * R(gsum))
+
+
+class IndBox(_FusedProx):
+    """Indicator of [lo, hi] (scalars or per-element CUDA vectors); prox = clamp (test/problems/test_nonconvex_qp.jl:19,33)."""
+
+    kind = L.PB_PROX_BOX
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = lo, hi
+
+    def descriptor(self, R):
+        t = torch()
+        lo_v = self.lo if isinstance(self.lo, t.Tensor) else None
+        hi_v = self.hi if isinstance(self.hi, t.Tensor) else None
+        return L.pb_prox(
+            L.PB_PROX_BOX, 0,
+            0.0 if lo_v is not None else float(R(self.lo)),
+            0.0 if hi_v is not None else float(R(self.hi)),
+            lo_v.data_ptr() if lo_v is not None else None,
+            hi_v.data_ptr() if hi_v is not None else None,
+        )
+
+
+class NormL21(_FusedProx):
+    """g(X) = lambda * sum_j ||X[:, j]||_2 over contiguous groups of `group` entries (NormL21(lambda, 1) on a
+    group x ngroups column-major matrix).  Shards must hold whole groups."""
+
+    kind = L.PB_PROX_L21
+
+    def __init__(self, lam=1.0, group=128):
+        if lam < 0:
+            raise ValueError("parameter lambda must be nonnegative")
+        self.lam, self.group = lam, int(group)
+
+    def descriptor(self, R):
+        return L.pb_prox(L.PB_PROX_L21, self.group, float(R(self.lam)), 0.0, None, None)
+
+    def value_from(self, R, gsum):
+        return R(R(self.lam) * R(gsum))
+
+
+class IndBallL2:
+    """Indicator of {||x||_2 <= r}.  Two-phase prox (global norm, then scale): not single-pass fusable
+    (SURVEY.md section 7 hard part 7).  Phase 1 = pb_forward / pb_nrm2sq (AUX = ||y||^2, combined across shards), phase 2 = the
+    fused step with PB_PROX_SCALE."""
+
+    fused = False
+    kind = L.PB_PROX_SCALE
+
+    def __init__(self, r=1.0):
+        if r <= 0:
+            raise ValueError("parameter r must be positive")
+        self.r = r
+
+    def scale_factor(self, R, ysq):
+        ny = R(np.sqrt(np.float64(ysq)))
+        with np.errstate(divide="ignore"):
+            return R(R(self.r) / ny)          # scal > 1  <=>  y is inside the ball: kernel copies y
+
+    def scale_descriptor(self, R, ysq):
+        return L.pb_prox(L.PB_PROX_SCALE, 0, float(self.scale_factor(R, ysq)), 0.0, None, None)
+
+    def prox_(self, z, y, gamma, comm=None):
+        ctx = Context.get(y.device)
+        R = real_type(y.dtype)
+        L.check(ctx.lib.pb_nrm2sq(ctx.h, pb_dtype(R), y.numel(), ptr(y)))
+        sc = (comm or LocalComm()).exchange(ctx)
+        d = self.scale_descriptor(R, sc.aux)
+        L.check(ctx.lib.pb_prox_apply(ctx.h, pb_dtype(R), y.numel(), ptr(y), float(gamma), C.byref(d), ptr(z)))
+        return R(0)
+
+    def value_from(self, R, gsum):
+        return R(0)

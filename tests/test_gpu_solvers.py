@@ -1,0 +1,215 @@
+"""GPU parity, solver level: the product's ForwardBackward / FastForwardBackward (fused CUDA path through the C ABI)
+against the CPU oracle on the reference's own problems.
+
+Bars: fp64 -- IDENTICAL iteration count, converged iterate within 1e-9*max(1,||z||inf), relative objective gap <= 1e-10;
+fp32 -- iterate within 1e-4 (the reference's own Float32 TOL, test/problems/test_lasso_small.jl:44), iteration count
+within +-1 % (+-2)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import proxb200 as pa  # noqa: E402
+from oracle import fb_oracle as o  # noqa: E402
+
+from conftest import load_golden  # noqa: E402
+
+TYPES = [np.float64, np.float32]
+
+
+def _objective(A, b, lam, v):
+    v = np.asarray(v, dtype=np.float64)
+    r = A.astype(np.float64) @ v - b.astype(np.float64)
+    return 0.5 * r @ r + float(lam) * np.abs(v).sum()
+
+
+def _unit_problem(T):
+    d = load_golden("unit_lasso_4x5")
+    A = np.asfortranarray(d["A"].astype(T))
+    b = d["b"].astype(T)
+    lam = T(0.1) * o.norm_inf(A.T @ b)
+    Lf = T(np.linalg.norm(d["A"], 2)) ** 2
+    return A, b, lam, Lf, d["xstar"].astype(T)
+
+
+CASES_UNIT = [
+    ("fb_fixed", "fb", dict(use_Lf=True), 150),
+    ("fb_adaptive", "fb", dict(adaptive=True), 300),
+    ("fb_regret", "fb", dict(adaptive=True, increase_gamma=1.01), 150),
+    ("ffb_fixed", "ffb", dict(use_Lf=True), 100),
+    ("ffb_adaptive", "ffb", dict(adaptive=True), 200),
+    ("ffb_regret", "ffb", dict(adaptive=True, increase_gamma=1.01), 100),
+    ("ffb_custom", "ffb", dict(use_Lf=True, custom=True), 100),
+]
+
+
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("name,alg,kw,bound", CASES_UNIT)
+def test_lasso_small_like_the_reference(T, name, alg, kw, bound):
+    """test/problems/test_lasso_small.jl:46-135 run on the GPU path, plus equality with the oracle's iteration count."""
+    A, b, lam, Lf, xstar = _unit_problem(T)
+    TOL = T(1e-4)
+    kw_o, kw_g = {}, {}
+    if kw.get("use_Lf"):
+        kw_o["Lf"] = kw_g["Lf"] = Lf
+    if kw.get("adaptive"):
+        kw_o["adaptive"] = kw_g["adaptive"] = True
+    if "increase_gamma" in kw:
+        kw_o["increase_gamma"] = kw_g["increase_gamma"] = T(kw["increase_gamma"])
+    if kw.get("custom"):
+        kw_o["extrapolation_sequence"] = o.fixed_nesterov_sequence(T)
+        kw_g["extrapolation_sequence"] = pa.FixedNesterovSequence(T)
+    x0 = np.zeros(5, T)
+    solver_o = o.fast_forward_backward if alg == "ffb" else o.forward_backward
+    z_o, it_o = solver_o(x0, o.LeastSquares(A, b), o.NormL1(lam), tol=TOL, **kw_o)
+    solver = (pa.FastForwardBackward if alg == "ffb" else pa.ForwardBackward)(tol=TOL)
+    x, it = solver(x0=x0, f=pa.LeastSquares(A, b), g=pa.NormL1(lam), **kw_g)
+    assert isinstance(x, np.ndarray) and x.dtype == T
+    assert np.max(np.abs(x - xstar)) <= TOL
+    assert it < bound
+    assert np.all(x0 == 0)
+    if T == np.float64:
+        assert it == it_o
+        assert np.max(np.abs(x - z_o)) <= 1e-9
+    else:
+        assert abs(it - it_o) <= max(2, it_o // 100)
+        assert np.max(np.abs(x - z_o)) <= 1e-4
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_lasso_strongly_convex_like_the_reference(T):
+    """test/problems/test_lasso_small_strongly_convex.jl:65-144."""
+    d = load_golden("unit_lasso_sc_5x5")
+    A = np.asfortranarray(d["A"].astype(T))
+    b, xstar, x0 = d["b"].astype(T), d["xstar"].astype(T), d["x0"].astype(T)
+    lam, mf, Lf = T(d["lam"]), T(d["mf"]), T(d["Lf"])
+    TOL = T(1e-4)
+    x0_backup = x0.copy()
+    f, g = pa.LeastSquares(A, b), pa.NormL1(lam)
+    runs = [
+        (pa.ForwardBackward(tol=TOL), dict(Lf=Lf), 110),
+        (pa.ForwardBackward(tol=TOL, adaptive=True), {}, 300),
+        (pa.ForwardBackward(tol=TOL, adaptive=True, increase_gamma=T(1.01)), {}, 80),
+        (pa.FastForwardBackward(tol=TOL), dict(Lf=Lf, mf=mf), 35),
+        (pa.FastForwardBackward(tol=TOL, adaptive=True), {}, 100),
+        (pa.FastForwardBackward(tol=TOL, adaptive=True, increase_gamma=T(1.01)), {}, 100),
+        (pa.FastForwardBackward(tol=TOL), dict(gamma=T(1) / Lf, mf=mf,
+                                              extrapolation_sequence=pa.ConstantNesterovSequence(mf, T(1) / Lf)), 35),
+    ]
+    for solver, kw, bound in runs:
+        y, it = solver(x0=x0, f=f, g=g, **kw)
+        assert y.dtype == T and np.max(np.abs(y - xstar)) <= TOL and it < bound
+        assert np.array_equal(x0, x0_backup)
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "medium"])
+@pytest.mark.parametrize("alg", ["ffb", "fb"])
+def test_benchmark_fixtures_iteration_count_and_objective(name, alg):
+    """benchmark/benchmarks.jl:47-61 (fp64, tol 1e-6, x0 = 0, adaptive): identical iteration count to the oracle,
+    objective gap <= 1e-10 vs the oracle and <= 1e-6 vs the fixture's xstar."""
+    d = load_golden("lasso_" + name)
+    A, b, lam, xstar = d["A"], d["b"], d["lam"], d["xstar"]
+    n = A.shape[1]
+    solver_o = o.fast_forward_backward if alg == "ffb" else o.forward_backward
+    z_o, it_o = solver_o(np.zeros(n), o.LeastSquares(A, b), o.NormL1(lam), tol=1e-6)
+    solver = (pa.FastForwardBackward if alg == "ffb" else pa.ForwardBackward)(tol=1e-6)
+    z, it = solver(x0=np.zeros(n), f=pa.LeastSquares(A, b), g=pa.NormL1(lam))
+    assert it == it_o
+    assert np.max(np.abs(z - z_o)) <= 1e-9 * max(1.0, np.max(np.abs(z_o)))
+    obj, obj_o, obj_s = _objective(A, b, lam, z), _objective(A, b, lam, z_o), _objective(A, b, lam, xstar)
+    assert abs(obj - obj_o) / obj_o <= 1e-10
+    if it < 10000:
+        assert abs(obj - obj_s) / obj_s <= 1e-6
+        assert np.max(np.abs(z - xstar)) <= 2 * np.max(np.abs(z_o - xstar)) + 1e-12
+    last = solver.last_state
+    assert float(last.gamma) > 0 and last.z.is_cuda
+
+
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("alg", ["ffb", "fb"])
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_state_by_state_equivalence_with_oracle(T, alg, adaptive):
+    """The pattern of test/problems/test_equivalence.jl:71-83: step two implementations side by side and compare the
+    states.  fp64: z, x, gamma agree to ~1e-13; lazily materialised y and res equal x - gamma*grad and x - z bit for bit."""
+    d = load_golden("lasso_small")
+    A, b, lam = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T), T(d["lam"])
+    n = A.shape[1]
+    kw = {} if adaptive else dict(Lf=T(np.linalg.norm(d["A"], 2) ** 2))
+    It_o = o.FastForwardBackwardIteration if alg == "ffb" else o.ForwardBackwardIteration
+    It_g = pa.FastForwardBackwardIteration if alg == "ffb" else pa.ForwardBackwardIteration
+    it_o = iter(It_o(np.zeros(n, T), o.LeastSquares(A, b), o.NormL1(lam), **kw))
+    it_g = iter(It_g(x0=np.zeros(n, T), f=pa.LeastSquares(A, b), g=pa.NormL1(lam), **kw))
+    tol = 1e-12 if T == np.float64 else 2e-5
+    for k in range(25):
+        so, sg = next(it_o), next(it_g)
+        assert type(sg.gamma) is T and type(sg.f_x) is T and type(sg.g_z) is T
+        assert np.isclose(float(sg.gamma), float(so.gamma), rtol=1e-12 if T == np.float64 else 1e-6)
+        scale = max(1.0, float(np.max(np.abs(so.z))))
+        assert np.max(np.abs(sg.z.cpu().numpy() - so.z)) <= tol * scale
+        assert np.max(np.abs(sg.x.cpu().numpy() - so.x)) <= tol * scale
+        assert np.isclose(float(sg.f_x), float(so.f_x), rtol=1e-11 if T == np.float64 else 1e-4)
+        assert np.isclose(float(sg.g_z), float(so.g_z), rtol=1e-11 if T == np.float64 else 1e-4, atol=1e-30)
+        xg, gg, zg = sg.x.cpu().numpy(), sg.grad_f_x.cpu().numpy(), sg.z.cpu().numpy()
+        assert np.array_equal(sg.y.cpu().numpy(), xg - sg.gamma * gg)
+        assert np.array_equal(sg.res.cpu().numpy(), xg - zg)
+        assert float(sg.res_norm_inf) == float(np.max(np.abs(xg - zg)))
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_box_qp_doc_example_and_user_callbacks(T):
+    """docs/src/guide/getting_started.jl:59-72 (analytic answer (2.3/3.4, 0)) with USER-DEFINED f and g plugged in through
+    the callback contract (value_and_gradient / prox!), like docs/src/guide/custom_objectives.jl:50-61,115-124."""
+    Q = torch.tensor([[3.4, 1.2], [1.2, 4.5]], dtype=torch.float64 if T == np.float64 else torch.float32, device="cuda")
+    q = torch.tensor([-2.3, 9.9], dtype=Q.dtype, device="cuda")
+
+    class Quadratic:                       # user smooth term: returns a fresh gradient, like the reference contract
+        calls = 0
+
+        def value_and_gradient(self, x):
+            Quadratic.calls += 1
+            g = Q @ x
+            return float(0.5 * (x @ g) + q @ x), g + q
+
+    class MyBox:                           # user proximable term: in-place prox!, returns g(z)
+        def prox_(self, z, y, gamma):
+            torch.clamp(y, 0.0, 1.0, out=z)
+            return 0.0
+
+    ffb = pa.FastForwardBackward(maxit=1000, tol=1e-5)
+    sol, it = ffb(x0=np.ones(2, T), f=Quadratic(), g=MyBox())
+    assert np.allclose(sol, [2.3 / 3.4, 0.0], atol=1e-4) and it < 1000 and Quadratic.calls > it
+    # the same problem with the built-in fused IndBox gives the same iterates
+    sol2, it2 = ffb(x0=np.ones(2, T), f=Quadratic(), g=pa.IndBox(0, 1))
+    assert it2 == it and np.allclose(sol2, sol, atol=1e-6)
+    # torch CUDA x0 in -> CUDA tensor out, x0 untouched
+    x0 = torch.ones(2, dtype=Q.dtype, device="cuda")
+    sol3, it3 = ffb(x0=x0, f=Quadratic(), g=pa.IndBox(0, 1))
+    assert sol3.is_cuda and it3 == it and torch.all(x0 == 1)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_ball_and_group_lasso_converge_to_oracle(T):
+    rng = np.random.default_rng(0)
+    m, n = 60, 256
+    A = np.asfortranarray(rng.standard_normal((m, n)).astype(T) / np.sqrt(m))
+    b = rng.standard_normal(m).astype(T)
+    Lf = T(np.linalg.norm(A.astype(np.float64), 2) ** 2)
+    tol = T(1e-5 if T == np.float64 else 1e-4)
+    for g_o, g_g in [(o.IndBallL2(T(0.5)), pa.IndBallL2(T(0.5))), (o.NormL21(T(0.3), 16), pa.NormL21(T(0.3), 16))]:
+        z_o, it_o = o.fast_forward_backward(np.zeros(n, T), o.LeastSquares(A, b), g_o, tol=tol, Lf=Lf, maxit=3000)
+        z, it = pa.FastForwardBackward(tol=tol, maxit=3000)(x0=np.zeros(n, T), f=pa.LeastSquares(A, b), g=g_g, Lf=Lf)
+        assert abs(it - it_o) <= max(2, it_o // 50)
+        assert np.max(np.abs(z - z_o)) <= (1e-7 if T == np.float64 else 2e-3)
+
+
+def test_verbose_display_and_maxit(capsys):
+    """test/problems/test_verbose.jl: verbose runs print `it | gamma | residual` rows; maxit caps the loop."""
+    d = load_golden("lasso_tiny")
+    solver = pa.ForwardBackward(tol=1e-6, maxit=50, verbose=True, freq=10)
+    z, it = solver(x0=np.zeros(10), f=pa.LeastSquares(d["A"], d["b"]), g=pa.NormL1(d["lam"]))
+    out = capsys.readouterr().out.strip().splitlines()
+    assert it == 50 and len(out) == 5 and out[0].split("|")[0].strip() == "10"
