@@ -99,8 +99,15 @@ double* pb_ctx_scalars_dev(pb_ctx* ctx);
 /* Redirect the scalar block to caller-owned device memory (PB_NSCALARS doubles, e.g. a framework tensor that is the
  * send buffer of the per-iteration all-gather).  NULL restores the context's own block. */
 int pb_ctx_set_scalars_dev(pb_ctx* ctx, double* dev);
-/* Launch shape knobs (0 keeps the default): CTAs per SM for streaming kernels; streaming cache hints on/off (-1 = auto by size). */
-int pb_ctx_set_launch(pb_ctx* ctx, int ctas_per_sm, int stream_hints);
+/* Tuning knobs of the streaming kernels (results never depend on them; tests sweep them to prove it). */
+enum {
+  PB_OPT_CTAS_PER_SM = 0,   /* CTAs per SM of the grid-stride kernels; 0 = per-kernel default                      */
+  PB_OPT_STREAM_HINTS = 1,  /* ld/st cache-streaming hints: -1 = auto (on when the working set exceeds L2), 0, 1   */
+  PB_OPT_UNROLL = 2,        /* 16-byte packs in flight per thread and input stream: 0 = default, or 1, 2, 4, 8       */
+  PB_OPT_STEP_IMPL = 3      /* fused step implementation: 0 = default, 1 = register (LDG) pipeline, 2 = TMA bulk-copy
+                               shared-memory ring                                                                 */
+};
+int pb_ctx_set_option(pb_ctx* ctx, int option, int value);
 /* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
 int64_t pb_ctx_launch_count(pb_ctx* ctx);
 

@@ -31,6 +31,8 @@ struct pb_ctx {
   size_t l2_bytes;
   int ctas_per_sm;     // 0 = per-kernel default
   int stream_hints;    // -1 auto, 0 off, 1 on
+  int unroll;          // 0 = default
+  int step_impl;       // 0 = default, 1 = register pipeline, 2 = TMA bulk ring
   double* scalars_dev;   // active scalar block (own or caller supplied)
   double* scalars_own;
   double* scalars_host;  // pinned mirror

@@ -110,13 +110,29 @@ extern "C" int pb_ctx_sync(pb_ctx* c) {
   return PB_OK;
 }
 
-extern "C" int pb_ctx_set_launch(pb_ctx* c, int ctas_per_sm, int stream_hints) {
+extern "C" int pb_ctx_set_option(pb_ctx* c, int option, int value) {
   PB_REQUIRE(c != nullptr, "null context");
-  PB_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 32, "ctas_per_sm out of range [0, 32]");
-  PB_REQUIRE(stream_hints >= -1 && stream_hints <= 1, "stream_hints must be -1, 0 or 1");
-  c->ctas_per_sm = ctas_per_sm;
-  c->stream_hints = stream_hints;
-  return PB_OK;
+  switch (option) {
+    case PB_OPT_CTAS_PER_SM:
+      PB_REQUIRE(value >= 0 && value <= 32, "ctas_per_sm out of range [0, 32]");
+      c->ctas_per_sm = value;
+      return PB_OK;
+    case PB_OPT_STREAM_HINTS:
+      PB_REQUIRE(value >= -1 && value <= 1, "stream_hints must be -1, 0 or 1");
+      c->stream_hints = value;
+      return PB_OK;
+    case PB_OPT_UNROLL:
+      PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8, "unroll must be 0, 1, 2, 4 or 8");
+      c->unroll = value;
+      return PB_OK;
+    case PB_OPT_STEP_IMPL:
+      PB_REQUIRE(value >= 0 && value <= 2, "step implementation must be 0, 1 or 2");
+      c->step_impl = value;
+      return PB_OK;
+    default:
+      pb_set_error("pb_ctx_set_option: unknown option %d", option);
+      return PB_EINVAL;
+  }
 }
 
 int pb_ensure_scratch(pb_ctx* c, size_t bytes) {

@@ -4,66 +4,7 @@
 // input array in flight per thread, grid sized as a multiple of the SM count, per-thread double(-double) accumulators,
 // warp-shuffle -> shared -> last-CTA reduction (common.cuh).  All of them are bandwidth bound (1-3 flop/byte), so no
 // tensor-core path exists for this file.
-#include "common.cuh"
-
-// ----------------------------------------------------------------------------------------------------------------
-// element-wise prox (ProximalOperators.jl semantics, restated from the package's published algorithm)
-// ----------------------------------------------------------------------------------------------------------------
-template <typename T, int PROX>
-__device__ __forceinline__ T prox_elem(T y, T a, T b) {
-  if constexpr (PROX == PB_PROX_L1) {
-    // z = y + (y <= -gl ? gl : (y >= gl ? -gl : -y)),  a = gl = gamma*lambda
-    T sel = (y <= -a) ? a : ((y >= a) ? -a : -y);
-    return add_rn(y, sel);
-  } else if constexpr (PROX == PB_PROX_BOX) {
-    return (y < a) ? a : ((y > b) ? b : y);
-  } else if constexpr (PROX == PB_PROX_SCALE) {
-    return (a > T(1)) ? y : mul_rn(a, y);
-  } else {
-    return y;
-  }
-}
-
-struct StepParams {
-  const void* x;
-  const void* grad;
-  const void* z_prev;
-  void* y;
-  void* z;
-  void* res;
-  void* x_next;
-  const void* lo_v;
-  const void* hi_v;
-  int64_t n;
-  double gamma, beta, a, b;  // a, b: prox parameters already combined on the host in the element type
-  PbWorkspace* ws;
-  double* out;
-};
-
-template <typename T, int PROX, bool EXTRAP>
-struct StepElem {
-  // processes one element, updates accumulators; returns z and (optionally) writes y, res, x_next through references
-  template <bool COMP>
-  static __device__ __forceinline__ void run(T x, T g, T zp, T lo, T hi, T gamma, T beta, T& y, T& z, T& r, T& xn,
-                                             Acc<3, 1>& acc) {
-    y = sub_rn(x, mul_rn(gamma, g));
-    z = prox_elem<T, PROX>(y, lo, hi);
-    r = sub_rn(x, z);
-    if constexpr (EXTRAP) xn = add_rn(z, mul_rn(beta, sub_rn(z, zp)));
-    const double rd = (double)r, gd = (double)g;
-    if constexpr (COMP) {
-      if constexpr (PROX == PB_PROX_L1) dd_add(acc.s[0], fabs((double)z));
-      dd_add_prod(acc.s[1], rd, rd);
-      dd_add_prod(acc.s[2], gd, rd);
-    } else {
-      // float data: the products are exact in double; plain double accumulation per thread, double-double across threads
-      if constexpr (PROX == PB_PROX_L1) acc.s[0].hi += fabs((double)z);
-      acc.s[1].hi = __fma_rn(rd, rd, acc.s[1].hi);
-      acc.s[2].hi = __fma_rn(gd, rd, acc.s[2].hi);
-    }
-    acc.m[0] = nanmax(acc.m[0], fabs(rd));
-  }
-};
+#include "step_common.cuh"
 
 template <typename T, int PROX, bool EXTRAP, int VEC, int UNROLL, bool HINT>
 __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
@@ -436,11 +377,9 @@ static bool use_hints(const pb_ctx* ctx, int64_t n, size_t elt, int nvec) {
   return (size_t)n * elt * nvec > ctx->l2_bytes;  // working set cannot live in L2: stream through it
 }
 
-template <typename T, int PROX, bool EXTRAP>
-static int launch_step_t(pb_ctx* ctx, const StepParams& p, bool vec_ok) {
+template <typename T, int PROX, bool EXTRAP, int UNROLL>
+static int launch_step_u(pb_ctx* ctx, const StepParams& p, bool vec_ok, bool hint) {
   constexpr int VEC = 16 / sizeof(T);
-  constexpr int UNROLL = 4;
-  const bool hint = use_hints(ctx, p.n, sizeof(T), EXTRAP ? 5 : 3);
   if (vec_ok) {
     const int grid = pb_stream_grid(ctx, (int64_t)PB_BLOCK * VEC * UNROLL, p.n, 4);
     if (hint)
@@ -455,37 +394,67 @@ static int launch_step_t(pb_ctx* ctx, const StepParams& p, bool vec_ok) {
   return PB_OK;
 }
 
+template <typename T, int PROX, bool EXTRAP>
+static int launch_step_t(pb_ctx* ctx, const StepParams& p, bool vec_ok) {
+  const bool hint = use_hints(ctx, p.n, sizeof(T), EXTRAP ? 5 : 3);
+  // the unroll sweep exists for the two headline prox kinds only (keeps the binary small)
+  if constexpr (PROX == PB_PROX_L1 || PROX == PB_PROX_BOX) {
+    switch (ctx->unroll) {
+      case 1: return launch_step_u<T, PROX, EXTRAP, 1>(ctx, p, vec_ok, hint);
+      case 2: return launch_step_u<T, PROX, EXTRAP, 2>(ctx, p, vec_ok, hint);
+      case 8: return launch_step_u<T, PROX, EXTRAP, 8>(ctx, p, vec_ok, hint);
+      default: break;
+    }
+  }
+  return launch_step_u<T, PROX, EXTRAP, 4>(ctx, p, vec_ok, hint);
+}
+
 template <typename T, bool EXTRAP>
 static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool vec_ok) {
   const T gamma = (T)p.gamma;
+  // prox parameters in the element type
   switch (g->kind) {
     case PB_PROX_ZERO:
-      return launch_step_t<T, PB_PROX_ZERO, EXTRAP>(ctx, p, vec_ok);
+      break;
     case PB_PROX_L1:
-      p.a = (double)mul_rn_host(gamma, (T)g->p0);
-      return launch_step_t<T, PB_PROX_L1, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_L21:
+      p.a = (double)mul_rn_host(gamma, (T)g->p0);   // gl = gamma*lambda, one rounding in R like the package
+      break;
     case PB_PROX_BOX:
       p.a = g->p0;
       p.b = g->p1;
       p.lo_v = g->v0;
       p.hi_v = g->v1;
       if ((p.lo_v && !pb_aligned16(p.lo_v)) || (p.hi_v && !pb_aligned16(p.hi_v))) vec_ok = false;
-      return launch_step_t<T, PB_PROX_BOX, EXTRAP>(ctx, p, vec_ok);
+      break;
     case PB_PROX_SCALE:
       p.a = g->p0;
-      return launch_step_t<T, PB_PROX_SCALE, EXTRAP>(ctx, p, vec_ok);
-    case PB_PROX_L21: {
-      PB_REQUIRE(g->group > 0 && p.n % g->group == 0, "NormL21 group must divide n");
-      p.a = (double)mul_rn_host(gamma, (T)g->p0);
-      const int64_t ngroups = p.n / g->group;
-      const int grid = pb_stream_grid(ctx, PB_BLOCK / 32, ngroups, 8);
-      k_step_l21<T, EXTRAP><<<grid, PB_BLOCK, 0, ctx->stream>>>(p, g->group);
-      PB_LAUNCH_CHECK(ctx);
-      return PB_OK;
-    }
+      break;
     default:
       pb_set_error("unknown prox kind %d", g->kind);
       return PB_EINVAL;
+  }
+  if (g->kind == PB_PROX_L21) {
+    PB_REQUIRE(g->group > 0 && p.n % g->group == 0, "NormL21 group must divide n");
+    const int64_t ngroups = p.n / g->group;
+    const int grid = pb_stream_grid(ctx, PB_BLOCK / 32, ngroups, 8);
+    k_step_l21<T, EXTRAP><<<grid, PB_BLOCK, 0, ctx->stream>>>(p, g->group);
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+  }
+  if (ctx->step_impl == 2 && vec_ok) {
+    const int rc = pb_launch_step_tma(ctx, sizeof(T) == 4 ? PB_F32 : PB_F64, g->kind, EXTRAP, p);
+    if (rc != PB_EUNSUPPORTED) return rc;
+  }
+  switch (g->kind) {
+    case PB_PROX_ZERO:
+      return launch_step_t<T, PB_PROX_ZERO, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_L1:
+      return launch_step_t<T, PB_PROX_L1, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_BOX:
+      return launch_step_t<T, PB_PROX_BOX, EXTRAP>(ctx, p, vec_ok);
+    default:
+      return launch_step_t<T, PB_PROX_SCALE, EXTRAP>(ctx, p, vec_ok);
   }
 }
 
@@ -498,7 +467,7 @@ static int step_common(pb_ctx* ctx, int dtype, int64_t n, const void* x, const v
   PB_REQUIRE(g != nullptr, "null prox descriptor");
   PB_REQUIRE(n == 0 || (x && grad && z), "null vector");
   PB_REQUIRE(!extrap || n == 0 || (z_prev && x_next), "null z_prev / x_next");
-  PB_REQUIRE(!extrap || x_next != x, "x_next must not alias x");
+  PB_REQUIRE(!extrap || n == 0 || x_next != x, "x_next must not alias x");
   StepParams p;
   p.x = x;
   p.grad = grad;

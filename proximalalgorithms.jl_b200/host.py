@@ -199,8 +199,10 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.pb_ctx_launch_count(self.h))
 
-    def set_launch(self, ctas_per_sm=0, stream_hints=-1):
-        L.check(self.lib.pb_ctx_set_launch(self.h, ctas_per_sm, stream_hints))
+    def set_launch(self, ctas_per_sm=0, stream_hints=-1, unroll=0, step_impl=0):
+        for opt, val in ((L.PB_OPT_CTAS_PER_SM, ctas_per_sm), (L.PB_OPT_STREAM_HINTS, stream_hints), (L.PB_OPT_UNROLL, unroll),
+                         (L.PB_OPT_STEP_IMPL, step_impl)):
+            L.check(self.lib.pb_ctx_set_option(self.h, opt, val))
 
     def sync(self):
         L.check(self.lib.pb_ctx_sync(self.h))

@@ -47,7 +47,17 @@ def _check_scalars(T, row, z, res, g, gfun_value):
 @pytest.mark.parametrize("T", TYPES)
 @pytest.mark.parametrize("n", SIZES)
 @pytest.mark.parametrize("prox", ["l1", "box", "zero", "scale_in", "scale_out"])
-def test_fb_and_ffb_step_bit_exact(T, n, prox):
+@pytest.mark.parametrize("impl", [1, 2])
+def test_fb_and_ffb_step_bit_exact(T, n, prox, impl):
+    """impl 1 = register (LDG) pipeline, impl 2 = TMA bulk-copy shared-memory ring: same bits."""
+    G.ctx().set_launch(step_impl=impl)
+    try:
+        _run_step_bit_exact(T, n, prox)
+    finally:
+        G.ctx().set_launch()
+
+
+def _run_step_bit_exact(T, n, prox):
     x, g, zp = _inputs(T, n)
     gamma, beta = T(0.37), T(0.81)
     if prox == "l1":
@@ -218,13 +228,13 @@ def test_reductions_independent_of_grid_size_and_hints():
         c = G.ctx()
         rows, zs = [], []
         try:
-            for ctas, hint in [(0, -1), (1, 0), (3, 1), (8, 0), (16, 1)]:
-                c.set_launch(ctas, hint)
+            for ctas, hint, unroll, impl in [(0, -1, 0, 0), (1, 0, 1, 1), (3, 1, 2, 1), (8, 0, 8, 1), (16, 1, 4, 1), (2, 0, 0, 2), (3, 0, 0, 2)]:
+                c.set_launch(ctas, hint, unroll, impl)
                 _, z, _, xn, row = G.ffb_step(T, xd, gd, zpd, T(0.2), T(0.6), desc, want_y=False, want_res=False)
                 rows.append([G.pair(row, s) for s in (L.PB_S_GSUM, L.PB_S_RESSQ, L.PB_S_GDR)] + [row[L.PB_S_RESINF]])
                 zs.append(z.clone())
         finally:
-            c.set_launch(0, -1)
+            c.set_launch()
         for r in rows[1:]:
             assert r == rows[0]
         for z in zs[1:]:
