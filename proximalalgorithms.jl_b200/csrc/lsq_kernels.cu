@@ -108,6 +108,60 @@ __global__ void __launch_bounds__(PB_BLOCK) k_gemv_t(const T* __restrict__ A, in
   }
 }
 
+// grad = A' r for SHORT columns (mb <= 32 lanes x 4 packs): LPC lanes share one column, each lane owns up to KP 16-byte
+// packs of it (rows lane*VEC + k*LPC*VEC), the matching packs of r live in registers for the whole column chunk, a warp
+// handles 32/LPC columns per sweep, log2(LPC) shuffle steps finish a column.  One CTA = one chunk of columns of ONE block.
+template <typename T, int LPC, int KP>
+__global__ void __launch_bounds__(PB_BLOCK) k_gemv_t_sub(const T* __restrict__ A, int64_t lda, int64_t blk_stride,
+                                                         const T* __restrict__ r, T* __restrict__ grad, int64_t mb,
+                                                         int64_t nb, int64_t chunk_cols, int64_t chunks_per_blk) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int CPW = 32 / LPC;                     // columns per warp sweep
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPC, colw = lane / LPC;
+  const int64_t k = blockIdx.x / chunks_per_blk;
+  const int64_t c0 = (blockIdx.x % chunks_per_blk) * chunk_cols;
+  int64_t c1 = c0 + chunk_cols;
+  if (c1 > nb) c1 = nb;
+  const T* __restrict__ Ak = A + k * blk_stride;
+  const T* __restrict__ rk = r + k * mb;
+  const int64_t npk = mb / VEC;                     // packs per column (mb % VEC == 0 checked by the launcher)
+  Pack<T, VEC> rv[KP];
+#pragma unroll
+  for (int q = 0; q < KP; ++q) {
+    const int64_t pk = sub + (int64_t)q * LPC;
+    if (pk < npk)
+      rv[q] = *reinterpret_cast<const Pack<T, VEC>*>(rk + pk * VEC);
+    else
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) rv[q].v[e] = T(0);
+  }
+  constexpr int WARPS = PB_BLOCK / 32;
+  for (int64_t j = c0 + (int64_t)warp * CPW + colw; j < c1 + colw; j += (int64_t)WARPS * CPW) {
+    // (loop bound padded by colw so that all lanes of a warp iterate together; inactive columns contribute nothing)
+    const bool live = j < c1;
+    const T* __restrict__ a = Ak + (live ? j : c0) * lda;
+    Pack<T, VEC> av[KP];
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+      const int64_t pk = sub + (int64_t)q * LPC;
+      if (pk < npk) av[q] = ld_pack<T, VEC, true>(a + pk * VEC);
+    }
+    T acc = T(0);
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+      const int64_t pk = sub + (int64_t)q * LPC;
+      if (pk < npk) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc = fma(av[q].v[e], rv[q].v[e], acc);
+      }
+    }
+#pragma unroll
+    for (int off = LPC / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (live && sub == 0) grad[k * nb + j] = acc;
+  }
+}
+
 // SquaredDistance: grad = x - b, AUX = ||x - b||^2  -> k_ew OP_SUB lives in step_kernels.cu (pb_sub); thin alias here.
 extern "C" int pb_sqdist(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* b, void* grad) {
   return pb_sub(ctx, dtype, n, x, b, grad);
@@ -152,6 +206,37 @@ static int gradient_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
                       const T* r, T* grad) {
   const int64_t ncols = nblk * nb;
   if (ncols == 0) return PB_OK;
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int KP = 4;
+  const int64_t npk = mb / VEC;
+  const bool sub_ok = mb > 0 && mb % VEC == 0 && lda % VEC == 0 && blk_stride % VEC == 0 && npk <= 32 * KP &&
+                      pb_aligned16(A) && pb_aligned16(r);
+  if (sub_ok) {
+    int lpc = 1;
+    while ((int64_t)lpc * KP < npk) lpc <<= 1;
+    // chunk the columns of a block so that the grid covers the machine ~8x
+    int64_t chunks = ((int64_t)ctx->sm_count * 8 + nblk - 1) / nblk;
+    const int64_t min_chunk = 256;
+    if (chunks > (nb + min_chunk - 1) / min_chunk) chunks = (nb + min_chunk - 1) / min_chunk;
+    if (chunks < 1) chunks = 1;
+    const int64_t chunk_cols = (nb + chunks - 1) / chunks;
+    chunks = (nb + chunk_cols - 1) / chunk_cols;
+    const int64_t grid = nblk * chunks;
+    PB_REQUIRE(grid <= 0x7fffffffLL, "grid too large");
+#define PB_LAUNCH_SUB(L)                                                                                          \
+  k_gemv_t_sub<T, L, KP><<<(unsigned)grid, PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, r, grad, mb, nb, chunk_cols, chunks)
+    switch (lpc) {
+      case 1: PB_LAUNCH_SUB(1); break;
+      case 2: PB_LAUNCH_SUB(2); break;
+      case 4: PB_LAUNCH_SUB(4); break;
+      case 8: PB_LAUNCH_SUB(8); break;
+      case 16: PB_LAUNCH_SUB(16); break;
+      default: PB_LAUNCH_SUB(32); break;
+    }
+#undef PB_LAUNCH_SUB
+    PB_LAUNCH_CHECK(ctx);
+    return PB_OK;
+  }
   const int grid = pb_stream_grid(ctx, PB_BLOCK / 32, ncols, 8);
   k_gemv_t<T><<<grid, PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, r, grad, mb, nb, nblk);
   PB_LAUNCH_CHECK(ctx);

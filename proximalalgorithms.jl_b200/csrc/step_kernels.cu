@@ -377,18 +377,43 @@ static bool use_hints(const pb_ctx* ctx, int64_t n, size_t elt, int nvec) {
   return (size_t)n * elt * nvec > ctx->l2_bytes;  // working set cannot live in L2: stream through it
 }
 
+// grid = SMs x CTAs-per-SM, never more CTAs than are co-resident: a grid-stride kernel with a partial second wave would
+// serialise (measured: 592 CTAs at 3 resident/SM ran 4 % slower than 296).
+template <typename K>
+static int resident_grid(pb_ctx* ctx, K kern, int* occ_cache, int64_t work_per_cta, int64_t n, int default_per_sm) {
+  if (*occ_cache == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PB_BLOCK, 0) != cudaSuccess || occ < 1) occ = 1;
+    *occ_cache = occ;
+  }
+  int per_sm = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : default_per_sm;
+  if (per_sm > *occ_cache) per_sm = *occ_cache;
+  int64_t g = (int64_t)ctx->sm_count * per_sm;
+  int64_t need = (n + work_per_cta - 1) / work_per_cta;
+  if (need < 1) need = 1;
+  if (g > need) g = need;
+  if (g > PB_MAX_CTAS) g = PB_MAX_CTAS;
+  return (int)g;
+}
+
 template <typename T, int PROX, bool EXTRAP, int UNROLL>
 static int launch_step_u(pb_ctx* ctx, const StepParams& p, bool vec_ok, bool hint) {
   constexpr int VEC = 16 / sizeof(T);
+  static int occ[3] = {0, 0, 0};
   if (vec_ok) {
-    const int grid = pb_stream_grid(ctx, (int64_t)PB_BLOCK * VEC * UNROLL, p.n, 4);
-    if (hint)
-      k_step<T, PROX, EXTRAP, VEC, UNROLL, true><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
-    else
-      k_step<T, PROX, EXTRAP, VEC, UNROLL, false><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+    if (hint) {
+      auto kern = k_step<T, PROX, EXTRAP, VEC, UNROLL, true>;
+      const int grid = resident_grid(ctx, kern, &occ[0], (int64_t)PB_BLOCK * VEC * UNROLL, p.n, 2);
+      kern<<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+    } else {
+      auto kern = k_step<T, PROX, EXTRAP, VEC, UNROLL, false>;
+      const int grid = resident_grid(ctx, kern, &occ[1], (int64_t)PB_BLOCK * VEC * UNROLL, p.n, 2);
+      kern<<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+    }
   } else {
-    const int grid = pb_stream_grid(ctx, (int64_t)PB_BLOCK * UNROLL, p.n, 4);
-    k_step<T, PROX, EXTRAP, 1, UNROLL, false><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+    auto kern = k_step<T, PROX, EXTRAP, 1, UNROLL, false>;
+    const int grid = resident_grid(ctx, kern, &occ[2], (int64_t)PB_BLOCK * UNROLL, p.n, 4);
+    kern<<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
   }
   PB_LAUNCH_CHECK(ctx);
   return PB_OK;

@@ -195,7 +195,7 @@ def test_box_qp_doc_example_and_user_callbacks(T):
 def test_ball_and_group_lasso_converge_to_oracle(T):
     rng = np.random.default_rng(0)
     m, n = 60, 256
-    A = np.asfortranarray(rng.standard_normal((m, n)).astype(T) / np.sqrt(m))
+    A = np.asfortranarray((rng.standard_normal((m, n)) / np.sqrt(m)).astype(T))
     b = rng.standard_normal(m).astype(T)
     Lf = T(np.linalg.norm(A.astype(np.float64), 2) ** 2)
     tol = T(1e-5 if T == np.float64 else 1e-4)
