@@ -421,10 +421,17 @@ static int launch_step_u(pb_ctx* ctx, const StepParams& p, bool vec_ok, bool hin
 
 template <typename T, int PROX, bool EXTRAP>
 static int launch_step_t(pb_ctx* ctx, const StepParams& p, bool vec_ok) {
-  const bool hint = use_hints(ctx, p.n, sizeof(T), EXTRAP ? 5 : 3);
+  // defaults from the interleaved A/B on B200 (profiles/r01_tune_step.md): L1 -> 4 packs in flight with streaming hints,
+  // box -> 2 packs without hints; PB_OPT_UNROLL / PB_OPT_STREAM_HINTS override.
+  bool hint = use_hints(ctx, p.n, sizeof(T), EXTRAP ? 5 : 3);
+  int unroll = ctx->unroll;
+  if constexpr (PROX == PB_PROX_BOX) {
+    if (ctx->stream_hints < 0) hint = false;
+    if (unroll == 0) unroll = 2;
+  }
   // the unroll sweep exists for the two headline prox kinds only (keeps the binary small)
   if constexpr (PROX == PB_PROX_L1 || PROX == PB_PROX_BOX) {
-    switch (ctx->unroll) {
+    switch (unroll) {
       case 1: return launch_step_u<T, PROX, EXTRAP, 1>(ctx, p, vec_ok, hint);
       case 2: return launch_step_u<T, PROX, EXTRAP, 2>(ctx, p, vec_ok, hint);
       case 8: return launch_step_u<T, PROX, EXTRAP, 8>(ctx, p, vec_ok, hint);
@@ -467,7 +474,9 @@ static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool ve
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
   }
-  if (ctx->step_impl == 2 && vec_ok) {
+  // measured default: K2 (5 streams) -> register pipeline, K1 (3 streams) -> TMA bulk-copy ring
+  const int impl = ctx->step_impl != 0 ? ctx->step_impl : (EXTRAP ? 1 : 2);
+  if (impl == 2 && vec_ok && p.n >= (int64_t)1 << 16) {
     const int rc = pb_launch_step_tma(ctx, sizeof(T) == 4 ? PB_F32 : PB_F64, g->kind, EXTRAP, p);
     if (rc != PB_EUNSUPPORTED) return rc;
   }

@@ -172,7 +172,7 @@ static int launch_tma(pb_ctx* ctx, const StepParams& p) {
     PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int grid = pb_stream_grid(ctx, TILE, p.n, 3);
+  const int grid = pb_stream_grid(ctx, TILE, p.n, EXTRAP ? 3 : 2);   // co-resident by construction (<= 72 KB smem per CTA)
   kern<<<grid, TMA_BLOCK, smem, ctx->stream>>>(p);
   PB_LAUNCH_CHECK(ctx);
   return PB_OK;

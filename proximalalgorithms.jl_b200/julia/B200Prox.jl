@@ -1,0 +1,226 @@
+# B200Prox.jl -- reference-side binding of libproxb200.so (include/proxb200.h) for ProximalAlgorithms.jl v0.7.
+#
+# STATUS: UNVERIFIED IN THIS REPOSITORY'S CI.  Julia is not installed in the build image nor on the GPU box, so this file
+# has never been executed; it is the `ccall` shim a ProximalAlgorithms.jl maintainer would add (INTEGRATION.md walks
+# through it).  Everything it calls is exercised, with the same arguments and in the same order, by the Python host
+# (proximalalgorithms.jl_b200/algorithms.py), which IS tested against the oracle on B200 hardware.
+#
+# What it does: ProximalAlgorithms' structs are parametric in the array type `Tx`
+# (src/algorithms/fast_forward_backward.jl:44,60), and `Base.iterate(iter, state)` is an ordinary method.  We add a
+# device-vector type `B200Vector{T}` and specialise the two iterators on it, so that
+#
+#     x0 = B200Vector(ctx, zeros(Float32, n))
+#     f  = B200LeastSquares(ctx, A, b);  g = ProximalOperators.NormL1(lam)
+#     ProximalAlgorithms.FastForwardBackward(tol = 1f-6)(x0 = x0, f = f, g = g, Lf = Lf)
+#
+# runs the UNCHANGED driver loop (src/ProximalAlgorithms.jl:114-123) with one fused kernel per iteration.
+
+module B200Prox
+
+using LinearAlgebra
+using ProximalCore
+using ProximalOperators: NormL1, IndBox, IndBallL2, NormL21
+import ProximalAlgorithms
+import ProximalAlgorithms: FastForwardBackwardIteration, ForwardBackwardIteration, AdaptiveNesterovSequence
+
+const LIB = get(ENV, "PROXB200_LIB", joinpath(@__DIR__, "..", "lib", "libproxb200.so"))
+
+const PB_F32, PB_F64 = Cint(0), Cint(1)
+const PB_PROX_ZERO, PB_PROX_L1, PB_PROX_BOX, PB_PROX_SCALE, PB_PROX_L21 = Cint(0), Cint(1), Cint(2), Cint(3), Cint(4)
+const S_GSUM, S_RESSQ, S_GDR, S_RESINF, S_AUX = 1, 3, 5, 7, 9        # 1-based indices into the scalar block
+const NSCALARS = 16
+
+struct PbProx               # mirrors `struct pb_prox` (include/proxb200.h)
+    kind::Cint
+    group::Cint
+    p0::Cdouble
+    p1::Cdouble
+    v0::Ptr{Cvoid}
+    v1::Ptr{Cvoid}
+end
+
+pbdtype(::Type{Float32}) = PB_F32
+pbdtype(::Type{Float64}) = PB_F64
+
+function check(rc::Cint)
+    rc == 0 || error("libproxb200: ", unsafe_string(ccall((:pb_last_error, LIB), Cstring, ())))
+    return nothing
+end
+
+# ---- context ------------------------------------------------------------------------------------------------------
+mutable struct B200Context
+    h::Ptr{Cvoid}
+    scalars::Vector{Float64}
+    function B200Context(device::Integer = 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:pb_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), device, C_NULL, 0, h))
+        ctx = new(h[], zeros(Float64, NSCALARS))
+        finalizer(c -> ccall((:pb_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), ctx)
+        return ctx
+    end
+end
+
+"Copy the device scalar block to the host (the one synchronisation per iteration) and return it."
+function read_scalars!(ctx::B200Context)
+    check(ccall((:pb_read_scalars, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.h, ctx.scalars))
+    return ctx.scalars
+end
+pairsum(s, i) = s[i] + s[i+1]          # rounded value of a double-double pair
+
+# ---- device vector ------------------------------------------------------------------------------------------------
+mutable struct B200Vector{T<:Union{Float32,Float64}} <: AbstractVector{T}
+    ctx::B200Context
+    ptr::Ptr{Cvoid}
+    n::Int
+    function B200Vector{T}(ctx::B200Context, n::Integer) where {T}
+        p = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:pb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx.h, n * sizeof(T), p))
+        v = new{T}(ctx, p[], n)
+        finalizer(w -> ccall((:pb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), w.ctx.h, w.ptr), v)
+        return v
+    end
+end
+function B200Vector(ctx::B200Context, host::Vector{T}) where {T}
+    v = B200Vector{T}(ctx, length(host))
+    check(ccall((:pb_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx.h, v.ptr, host, sizeof(host)))
+    check(ccall((:pb_ctx_sync, LIB), Cint, (Ptr{Cvoid},), ctx.h))      # `host` may be collected after return
+    return v
+end
+Base.size(v::B200Vector) = (v.n,)
+Base.similar(v::B200Vector{T}) where {T} = B200Vector{T}(v.ctx, v.n)
+function Base.copy(v::B200Vector{T}) where {T}                      # fast_forward_backward.jl:74, forward_backward.jl:66
+    w = similar(v)
+    check(ccall((:pb_copy, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), v.ctx.h, w.ptr, v.ptr, v.n * sizeof(T)))
+    return w
+end
+function Base.zero(v::B200Vector{T}) where {T}
+    w = similar(v)
+    check(ccall((:pb_memset_zero, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), v.ctx.h, w.ptr, v.n * sizeof(T)))
+    return w
+end
+function Base.Array(v::B200Vector{T}) where {T}
+    host = Vector{T}(undef, v.n)
+    check(ccall((:pb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), v.ctx.h, host, v.ptr, sizeof(host)))
+    return host
+end
+Base.getindex(v::B200Vector, i::Int) = Array(v)[i]      # debugging only: every call is a full download
+
+function LinearAlgebra.norm(v::B200Vector{T}, p::Real = 2) where {T}
+    check(ccall((:pb_nrm2sq, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}), v.ctx.h, pbdtype(T), v.n, v.ptr))
+    s = read_scalars!(v.ctx)
+    p == Inf && return T(s[11])
+    p == 2 || error("B200Vector: only norm(., 2) and norm(., Inf) are accelerated")
+    return T(sqrt(pairsum(s, S_AUX)))
+end
+function LinearAlgebra.dot(a::B200Vector{T}, b::B200Vector{T}) where {T}
+    check(ccall((:pb_dot, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}), a.ctx.h, pbdtype(T), a.n, a.ptr, b.ptr))
+    return T(pairsum(read_scalars!(a.ctx), S_AUX))
+end
+
+# ---- proximable terms: descriptors for ProximalOperators' own types ---------------------------------------------------
+descriptor(::ProximalCore.Zero, ::Type) = PbProx(PB_PROX_ZERO, 0, 0.0, 0.0, C_NULL, C_NULL)
+descriptor(g::NormL1{<:Real}, ::Type{T}) where {T} = PbProx(PB_PROX_L1, 0, Float64(T(g.lambda)), 0.0, C_NULL, C_NULL)
+descriptor(g::IndBox{<:Real,<:Real}, ::Type{T}) where {T} = PbProx(PB_PROX_BOX, 0, Float64(T(g.lb)), Float64(T(g.ub)), C_NULL, C_NULL)
+descriptor(g::NormL21, ::Type{T}, group::Integer) where {T} = PbProx(PB_PROX_L21, Cint(group), Float64(T(g.lambda)), 0.0, C_NULL, C_NULL)
+value_from(g::NormL1, ::Type{T}, s) where {T} = T(g.lambda) * T(pairsum(s, S_GSUM))
+value_from(g, ::Type{T}, s) where {T} = zero(T)
+
+"prox!(z, g, y, gamma) -> g(z)   (ProximalCore contract; call sites fast_forward_backward.jl:80,141)"
+function ProximalCore.prox!(z::B200Vector{T}, g::Union{NormL1,IndBox,ProximalCore.Zero}, y::B200Vector{T}, gamma) where {T}
+    d = Ref(descriptor(g, T))
+    check(ccall((:pb_prox_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cdouble, Ref{PbProx}, Ptr{Cvoid}),
+                y.ctx.h, pbdtype(T), y.n, y.ptr, Float64(gamma), d, z.ptr))
+    return value_from(g, T, read_scalars!(y.ctx))
+end
+
+# ---- smooth term: dense least squares with the benchmark's explicit gradient (benchmark/benchmarks.jl:11-17) -----------
+struct B200LeastSquares{T}
+    ctx::B200Context
+    A::B200Vector{T}          # column-major m x n, as Julia stores it
+    b::B200Vector{T}
+    r::B200Vector{T}
+    m::Int
+    n::Int
+end
+function B200LeastSquares(ctx::B200Context, A::Matrix{T}, b::Vector{T}) where {T}
+    m, n = size(A)
+    return B200LeastSquares{T}(ctx, B200Vector(ctx, vec(A)), B200Vector(ctx, b), B200Vector{T}(ctx, m), m, n)
+end
+
+"Enqueue r = A x - b (AUX = ||r||^2) and grad = A' r; the value is read with the next scalar read-back."
+function value_and_gradient_into!(grad::B200Vector{T}, f::B200LeastSquares{T}, x::B200Vector{T}) where {T}
+    check(ccall((:pb_lsq_dense_residual, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                f.ctx.h, pbdtype(T), f.m, f.n, f.A.ptr, f.m, x.ptr, f.b.ptr, f.r.ptr))
+    check(ccall((:pb_lsq_dense_gradient, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                f.ctx.h, pbdtype(T), f.m, f.n, f.A.ptr, f.m, f.r.ptr, grad.ptr))
+    return nothing
+end
+lsq_value(::Type{T}, s) where {T} = (nr = T(sqrt(pairsum(s, S_AUX))); nr^2 / 2)      # norm(res)^2/2, sqrt-then-square
+
+function ProximalAlgorithms.value_and_gradient(f::B200LeastSquares{T}, x::B200Vector{T}) where {T}
+    grad = similar(x)
+    value_and_gradient_into!(grad, f, x)
+    return lsq_value(T, read_scalars!(f.ctx)), grad
+end
+
+# ---- FastForwardBackward specialised on B200Vector ----------------------------------------------------------------------
+# Own state type: same field names as FastForwardBackwardState (fast_forward_backward.jl:60-71); `y` and `res` are
+# materialised on demand (they cost 2 extra vector writes per iteration if always stored).
+mutable struct B200FFBState{R,T}
+    x::B200Vector{T}
+    f_x::R
+    grad_f_x::B200Vector{T}
+    gamma::R
+    z::B200Vector{T}
+    g_z::R
+    z_prev::B200Vector{T}
+    extrapolation_sequence::Any
+    x_next::B200Vector{T}
+    beta_next::R
+    res_inf::R
+end
+
+function fused_step!(st::B200FFBState{R,T}, g, beta) where {R,T}
+    d = Ref(descriptor(g, T))
+    check(ccall((:pb_ffb_step, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Ref{PbProx}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                st.x.ctx.h, pbdtype(T), st.x.n, st.x.ptr, st.grad_f_x.ptr, st.z_prev.ptr, Float64(st.gamma), Float64(beta), d,
+                C_NULL, st.z.ptr, C_NULL, st.x_next.ptr))
+    s = read_scalars!(st.x.ctx)                       # the single host sync of the iteration
+    st.g_z = value_from(g, T, s)
+    st.res_inf = R(s[S_RESINF])
+    return s
+end
+
+next_beta!(st::B200FFBState) = st.extrapolation_sequence isa AdaptiveNesterovSequence ?
+    ProximalAlgorithms.next!(st.extrapolation_sequence, st.gamma) : first(st.extrapolation_sequence)
+
+# init: fast_forward_backward.jl:73-97 (fixed stepsize: `gamma` or `Lf` given)
+function Base.iterate(iter::FastForwardBackwardIteration{R,<:B200Vector{T}}) where {R,T}
+    iter.gamma === nothing && error("B200Prox: adaptive stepsize is implemented in the Python host only; pass Lf or gamma")
+    x = copy(iter.x0)
+    grad = similar(x)
+    value_and_gradient_into!(grad, iter.f, x)
+    seq = iter.extrapolation_sequence !== nothing ? Iterators.Stateful(iter.extrapolation_sequence) : AdaptiveNesterovSequence(iter.mf)
+    st = B200FFBState{R,T}(x, zero(R), grad, R(iter.gamma), similar(x), zero(R), copy(x), seq, similar(x), zero(R), zero(R))
+    st.beta_next = next_beta!(st)
+    s = fused_step!(st, iter.g, st.beta_next)
+    st.f_x = lsq_value(R, s)
+    return st, st
+end
+
+# step: fast_forward_backward.jl:106-145; the extrapolation of :135 was produced by the previous fused pass
+function Base.iterate(iter::FastForwardBackwardIteration{R,<:B200Vector{T}}, st::B200FFBState{R,T}) where {R,T}
+    st.x, st.x_next = st.x_next, st.x                 # :135
+    st.z_prev, st.z = st.z, st.z_prev                 # :136
+    value_and_gradient_into!(st.grad_f_x, iter.f, st.x)      # :138-139
+    st.beta_next = next_beta!(st)
+    s = fused_step!(st, iter.g, st.beta_next)         # :140-142 (+ next :135)
+    st.f_x = lsq_value(R, s)
+    return st, st
+end
+
+ProximalAlgorithms.default_stopping_criterion(tol, ::FastForwardBackwardIteration, st::B200FFBState) = st.res_inf / st.gamma <= tol
+ProximalAlgorithms.default_solution(::FastForwardBackwardIteration, st::B200FFBState) = st.z
+
+end # module
