@@ -46,6 +46,9 @@ def parse():
     p.add_argument("--n", type=int, default=N_TOTAL)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--exchange", default="device", choices=["device", "nccl", "memcpy"],
+                   help="per-iteration scalar exchange: device = in-kernel NVLink push + pinned-flag poll (default); "
+                        "nccl = all_gather + D2H copy; memcpy = cudaMemcpy read-back (N=1 only)")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return p.parse_args()
 
@@ -196,7 +199,14 @@ def run_b200(args):
     from proxb200.host import Context, LocalComm, TorchDistComm, ptr, shard_bounds
 
     ctx = Context.get()
-    comm = TorchDistComm() if world > 1 else LocalComm()
+    from proxb200.host import DeviceExchangeComm
+
+    if args.exchange == "device":
+        comm = DeviceExchangeComm(ctx)
+    elif world > 1:
+        comm = TorchDistComm()
+    else:
+        comm = LocalComm()
     lo, hi = shard_bounds(args.n, world)[rank]
     n = hi - lo
     gen = torch.Generator(device="cuda").manual_seed(3 + rank)
@@ -264,10 +274,10 @@ def run_b200(args):
 
         def solve():
             f = pa.SquaredDistance(b_h)                        # H2D of b inside the timed region
-            return solver(x0=x0_h, f=f, g=pa.NormL1(LAMBDA), gamma=1.0, comm=comm if world > 1 else None, n_global=args.n)
+            return solver(x0=x0_h, f=f, g=pa.NormL1(LAMBDA), gamma=1.0, comm=comm, n_global=args.n)
 
         solver_w = pa.FastForwardBackward(maxit=3, tol=-1.0)
-        solver_w(x0=x0_h, f=pa.SquaredDistance(b_h), g=pa.NormL1(LAMBDA), gamma=1.0, comm=comm if world > 1 else None, n_global=args.n)
+        solver_w(x0=x0_h, f=pa.SquaredDistance(b_h), g=pa.NormL1(LAMBDA), gamma=1.0, comm=comm, n_global=args.n)
         barrier()
         t0 = time.perf_counter()
         zsol, its = solve()
@@ -323,7 +333,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": "M3 Lasso FISTA fused-step-only: n=1e8 fp32 total, NormL1(1), gamma=0.1, beta=0.5, gradient supplied as a resident buffer; "
                                    "step = pb_ffb_step + per-iteration scalar read-back" + (" (all-gather of the scalar block)" if world > 1 else ""),
-                       "n": args.n, "n_per_gpu": n, "parallelism": f"row-shard x{world}", "l2": "inputs exceed L2 (5 x %.0f MB streams per GPU)" % (4 * n / 1e6)},
+                       "n": args.n, "n_per_gpu": n, "parallelism": f"row-shard x{world}", "exchange": args.exchange, "l2": "inputs exceed L2 (5 x %.0f MB streams per GPU)" % (4 * n / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "kernel": "k_step<float, L1, EXTRAP> (pb_ffb_step)", "kernel_ms": kern_ms_max,
                          "algorithmic_bytes_per_launch": BYTES_PER_ELT * n, "peak_source": peak_src},

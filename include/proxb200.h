@@ -104,12 +104,31 @@ enum {
   PB_OPT_CTAS_PER_SM = 0,   /* CTAs per SM of the grid-stride kernels; 0 = per-kernel default                      */
   PB_OPT_STREAM_HINTS = 1,  /* ld/st cache-streaming hints: -1 = auto (on when the working set exceeds L2), 0, 1   */
   PB_OPT_UNROLL = 2,        /* 16-byte packs in flight per thread and input stream: 0 = default, or 1, 2, 4, 8       */
-  PB_OPT_STEP_IMPL = 3      /* fused step implementation: 0 = default, 1 = register (LDG) pipeline, 2 = TMA bulk-copy
+  PB_OPT_STEP_IMPL = 3,     /* fused step implementation: 0 = default, 1 = register (LDG) pipeline, 2 = TMA bulk-copy
                                shared-memory ring                                                                 */
+  PB_OPT_FUSED_EXCHANGE = 4 /* 1: pb_fb_step / pb_ffb_step also perform the per-iteration exchange (pb_xchg_*) in their
+                               last CTA, so the iteration needs no collective launch, memcpy or stream sync       */
 };
 int pb_ctx_set_option(pb_ctx* ctx, int option, int value);
 /* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
 int64_t pb_ctx_launch_count(pb_ctx* ctx);
+
+/* ---- C1: per-iteration exchange of the scalar block, by the GPU itself --------------------------------------------
+ * Replaces "NCCL all-gather + cudaMemcpy + stream synchronise" per iteration: each rank's reducing kernel pushes its
+ * PB_NSCALARS doubles to every peer over NVLink (peer stores into cudaIpc-mapped buffers), waits for the peers' rows and
+ * copies all rows into mapped pinned host memory; the host polls a flag there.  With world == 1 it is a zero-copy
+ * read-back.  Set-up: every rank calls pb_xchg_init (gets a PB_IPC_HANDLE_BYTES handle), the host framework all-gathers
+ * the handles (any transport), every rank calls pb_xchg_connect.  All ranks must issue the same sequence of exchanges. */
+#define PB_IPC_HANDLE_BYTES 64
+#define PB_MAX_WORLD 16
+int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out);
+int pb_xchg_connect(pb_ctx* ctx, const void* all_handles /* world x PB_IPC_HANDLE_BYTES, rank order */);
+int pb_xchg_shutdown(pb_ctx* ctx);
+/* Enqueue a stand-alone exchange of the current scalar block (for reads that do not follow a fused step). */
+int pb_exchange(pb_ctx* ctx);
+/* Wait for the most recent exchange (launching one if none is pending) and return the world x PB_NSCALARS rows in rank
+ * order.  Polls pinned memory: no CUDA call on the fast path. */
+int pb_exchange_wait(pb_ctx* ctx, double* rows_out, double timeout_s);
 
 /* ---- memory (lets a host without a CUDA binding own device vectors: Julia `B200Vector`) -------------------------- */
 int pb_malloc(pb_ctx* ctx, size_t bytes, void** dptr);

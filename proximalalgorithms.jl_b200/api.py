@@ -27,7 +27,7 @@ from .functions import (  # noqa: F401
     SquaredDistance,
     Zero,
 )
-from .host import Context, LocalComm, Scalars, TorchDistComm, shard_bounds  # noqa: F401
+from .host import Context, DeviceExchangeComm, LocalComm, Scalars, TorchDistComm, shard_bounds  # noqa: F401
 from .nesterov import (  # noqa: F401
     AdaptiveNesterovSequence,
     ConstantNesterovSequence,

@@ -8,6 +8,7 @@
 #include <stdio.h>
 
 #include "proxb200.h"
+#include "xchg.cuh"
 
 #define PB_BLOCK 256            // threads per CTA of every streaming kernel
 #define PB_MAX_CTAS 4096        // upper bound on grid size of reducing kernels (workspace rows)
@@ -44,7 +45,22 @@ struct pb_ctx {
   // cached device buffers of pb_ffb_step_host
   void* hbuf[5];
   size_t hbuf_bytes;
+  // C1 exchange (xchg.cu): own IPC-exported buffer, peer mappings, mapped pinned landing zone for the host
+  double* xchg_own;
+  double* xchg_peer[PB_MAX_RANKS];
+  double* xchg_host_rows;               // host pointer (pinned, mapped)
+  double* xchg_host_rows_dev;           // its device alias
+  unsigned long long* xchg_host_flag;   // host pointer
+  unsigned long long* xchg_host_flag_dev;
+  unsigned long long xchg_seq;          // last sequence number issued
+  int xchg_rank, xchg_world;            // world == 0: not initialised
+  int xchg_connected;
+  int xchg_fused;                       // K1/K2 push in-kernel
+  int xchg_pending;                     // a launched kernel will publish xchg_seq
 };
+
+// Fill the kernel-side parameters for the next in-kernel exchange (advances the sequence number); world = 0 if disabled.
+void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want);
 
 void pb_set_error(const char* fmt, ...);
 int pb_ensure_scratch(pb_ctx* ctx, size_t bytes);
@@ -190,7 +206,8 @@ __device__ __forceinline__ void block_reduce(Acc<NSUM, NMAX>& a) {
 // CTA partial -> workspace; the last CTA to arrive folds all partials in a fixed order (deterministic for a given
 // grid, and -- thanks to the double-double arithmetic -- equal after rounding for any grid) and writes the scalar block.
 template <int NSUM, int NMAX, int BLOCK>
-__device__ __forceinline__ void grid_reduce(Acc<NSUM, NMAX>& a, PbWorkspace* ws, double* out, const OutMap& map) {
+__device__ __forceinline__ void grid_reduce(Acc<NSUM, NMAX>& a, PbWorkspace* ws, double* out, const OutMap& map,
+                                            const XchgParams* xp = nullptr) {
   __shared__ bool is_last;
   block_reduce<NSUM, NMAX, BLOCK>(a);
   if (threadIdx.x == 0) {
@@ -232,6 +249,11 @@ __device__ __forceinline__ void grid_reduce(Acc<NSUM, NMAX>& a, PbWorkspace* ws,
     for (int k = 0; k < NMAX; ++k)
       if (map.max_slot[k] >= 0) out[map.max_slot[k]] = a.m[k];
     ws->ticket = 0;  // ready for the next launch on this stream
+  }
+  // fused C1: the CTA that produced the final scalars also exchanges them with the peers and hands them to the host
+  if (xp != nullptr && xp->world > 0) {
+    __syncthreads();
+    xchg_push_wait(*xp, out);
   }
 }
 

@@ -89,6 +89,7 @@ extern "C" int pb_ctx_destroy(pb_ctx* c) {
   if (!c) return PB_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  pb_xchg_shutdown(c);
   for (int k = 0; k < 5; ++k)
     if (c->hbuf[k]) cudaFree(c->hbuf[k]);
   if (c->scratch) cudaFree(c->scratch);
@@ -128,6 +129,11 @@ extern "C" int pb_ctx_set_option(pb_ctx* c, int option, int value) {
     case PB_OPT_STEP_IMPL:
       PB_REQUIRE(value >= 0 && value <= 2, "step implementation must be 0, 1 or 2");
       c->step_impl = value;
+      return PB_OK;
+    case PB_OPT_FUSED_EXCHANGE:
+      PB_REQUIRE(value == 0 || value == 1, "fused exchange must be 0 or 1");
+      PB_REQUIRE(value == 0 || (c->xchg_world > 0 && c->xchg_connected), "pb_xchg_init / pb_xchg_connect first");
+      c->xchg_fused = value;
       return PB_OK;
     default:
       pb_set_error("pb_ctx_set_option: unknown option %d", option);

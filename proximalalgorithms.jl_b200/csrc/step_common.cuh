@@ -35,6 +35,7 @@ struct StepParams {
   double gamma, beta, a, b;  // a, b: prox parameters already combined on the host in the element type
   PbWorkspace* ws;
   double* out;
+  XchgParams xchg;   // fused per-iteration exchange (world == 0: off)
 };
 
 template <typename T, int PROX, bool EXTRAP>

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
   map.sum_slot[3] = -1;
   map.max_slot[0] = PB_S_RESINF;
   map.max_slot[1] = -1;
-  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map);
+  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map, &p.xchg);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step_l21(StepParams p, int group) 
   map.sum_slot[3] = -1;
   map.max_slot[0] = PB_S_RESINF;
   map.max_slot[1] = -1;
-  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map);
+  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map, &p.xchg);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -517,6 +517,7 @@ static int step_common(pb_ctx* ctx, int dtype, int64_t n, const void* x, const v
   p.a = p.b = 0.0;
   p.ws = ctx->ws;
   p.out = ctx->scalars_dev;
+  pb_xchg_next(ctx, &p.xchg, ctx->xchg_fused != 0 && n > 0);
   bool vec_ok = pb_aligned16(x) && pb_aligned16(grad) && pb_aligned16(z) && (!y || pb_aligned16(y)) &&
                 (!res || pb_aligned16(res)) && (!extrap || (pb_aligned16(z_prev) && pb_aligned16(x_next)));
   if (dtype == PB_F32)

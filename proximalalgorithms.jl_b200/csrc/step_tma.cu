@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(TMA_BLOCK) k_step_tma(StepParams p) {
   map.sum_slot[3] = -1;
   map.max_slot[0] = PB_S_RESINF;
   map.max_slot[1] = -1;
-  grid_reduce<3, 1, TMA_BLOCK>(acc, p.ws, p.out, map);
+  grid_reduce<3, 1, TMA_BLOCK>(acc, p.ws, p.out, map, &p.xchg);
 }
 
 template <typename T, int PROX, bool EXTRAP>

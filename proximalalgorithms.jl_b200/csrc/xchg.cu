@@ -1,0 +1,157 @@
+// xchg.cu -- host side of C1 (see xchg.cuh): IPC set-up of the per-rank exchange buffers, the stand-alone 1-CTA exchange
+// kernel for reads that do not follow a fused step, and the host-side wait on the mapped pinned flag.
+#include <string.h>
+#include <time.h>
+
+#include "common.cuh"
+
+static_assert(sizeof(cudaIpcMemHandle_t) == PB_IPC_HANDLE_BYTES, "PB_IPC_HANDLE_BYTES must match cudaIpcMemHandle_t");
+
+__global__ void __launch_bounds__(PB_BLOCK) k_xchg(XchgParams xp, const double* local_block) {
+  xchg_push_wait(xp, local_block);
+}
+
+void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want) {
+  memset(xp, 0, sizeof(*xp));
+  if (!want || ctx->xchg_world <= 0 || !ctx->xchg_connected) return;
+  ctx->xchg_seq += 1;
+  ctx->xchg_pending = 1;
+  for (int r = 0; r < ctx->xchg_world; ++r) xp->peer[r] = ctx->xchg_peer[r];
+  xp->host_rows = ctx->xchg_host_rows_dev;
+  xp->host_flag = ctx->xchg_host_flag_dev;
+  xp->seq = ctx->xchg_seq;
+  xp->rank = ctx->xchg_rank;
+  xp->world = ctx->xchg_world;
+}
+
+extern "C" int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(world >= 1 && world <= PB_MAX_RANKS && rank >= 0 && rank < world, "need 0 <= rank < world <= 16");
+  PB_REQUIRE(ctx->xchg_world == 0, "exchange already initialised on this context");
+  PB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  PB_CHECK_CUDA(cudaMalloc(&ctx->xchg_own, PB_XCHG_BYTES));
+  PB_CHECK_CUDA(cudaMemset(ctx->xchg_own, 0, PB_XCHG_BYTES));
+  void* host = nullptr;
+  PB_CHECK_CUDA(cudaHostAlloc(&host, (size_t)PB_MAX_RANKS * PB_NSCALARS * 8 + 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(host, 0, (size_t)PB_MAX_RANKS * PB_NSCALARS * 8 + 64);
+  ctx->xchg_host_rows = static_cast<double*>(host);
+  ctx->xchg_host_flag = reinterpret_cast<unsigned long long*>(ctx->xchg_host_rows + PB_MAX_RANKS * PB_NSCALARS);
+  void* dev_alias = nullptr;
+  PB_CHECK_CUDA(cudaHostGetDevicePointer(&dev_alias, host, 0));
+  ctx->xchg_host_rows_dev = static_cast<double*>(dev_alias);
+  ctx->xchg_host_flag_dev = reinterpret_cast<unsigned long long*>(ctx->xchg_host_rows_dev + PB_MAX_RANKS * PB_NSCALARS);
+  ctx->xchg_rank = rank;
+  ctx->xchg_world = world;
+  ctx->xchg_seq = 0;
+  ctx->xchg_pending = 0;
+  ctx->xchg_connected = 0;
+  for (int r = 0; r < PB_MAX_RANKS; ++r) ctx->xchg_peer[r] = nullptr;
+  ctx->xchg_peer[rank] = ctx->xchg_own;
+  if (world == 1) ctx->xchg_connected = 1;
+  if (handle_out) {
+    cudaIpcMemHandle_t h;
+    if (world > 1) {
+      PB_CHECK_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg_own));
+    } else {
+      memset(&h, 0, sizeof(h));
+    }
+    memcpy(handle_out, &h, sizeof(h));
+  }
+  PB_CHECK_CUDA(cudaDeviceSynchronize());
+  return PB_OK;
+}
+
+extern "C" int pb_xchg_connect(pb_ctx* ctx, const void* all_handles) {
+  PB_REQUIRE(ctx != nullptr && ctx->xchg_world > 0, "pb_xchg_init first");
+  if (ctx->xchg_world == 1) return PB_OK;
+  PB_REQUIRE(all_handles != nullptr, "null handles");
+  PB_CHECK_CUDA(cudaSetDevice(ctx->device));
+  const unsigned char* hs = static_cast<const unsigned char*>(all_handles);
+  for (int r = 0; r < ctx->xchg_world; ++r) {
+    if (r == ctx->xchg_rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs + (size_t)r * PB_IPC_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    PB_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->xchg_peer[r] = static_cast<double*>(p);
+  }
+  ctx->xchg_connected = 1;
+  return PB_OK;
+}
+
+extern "C" int pb_xchg_shutdown(pb_ctx* ctx) {
+  if (!ctx || ctx->xchg_world == 0) return PB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < ctx->xchg_world; ++r)
+    if (r != ctx->xchg_rank && ctx->xchg_peer[r]) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
+  if (ctx->xchg_own) cudaFree(ctx->xchg_own);
+  if (ctx->xchg_host_rows) cudaFreeHost(ctx->xchg_host_rows);
+  ctx->xchg_own = nullptr;
+  ctx->xchg_host_rows = nullptr;
+  ctx->xchg_world = 0;
+  ctx->xchg_connected = 0;
+  ctx->xchg_fused = 0;
+  return PB_OK;
+}
+
+// Launch the stand-alone exchange of the current scalar block (used when the last reducing kernel was not a fused step).
+extern "C" int pb_exchange(pb_ctx* ctx) {
+  PB_REQUIRE(ctx != nullptr && ctx->xchg_world > 0 && ctx->xchg_connected, "exchange not initialised / connected");
+  XchgParams xp;
+  pb_xchg_next(ctx, &xp, true);
+  k_xchg<<<1, PB_BLOCK, 0, ctx->stream>>>(xp, ctx->scalars_dev);
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}
+
+static double now_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+// Wait (polling mapped pinned memory; no CUDA call on the fast path) for the most recently issued exchange and copy the
+// world x PB_NSCALARS rows to `rows_out` (rank order).  If no exchange is pending, one is launched first.
+extern "C" int pb_exchange_wait(pb_ctx* ctx, double* rows_out, double timeout_s) {
+  PB_REQUIRE(ctx != nullptr && rows_out != nullptr, "null argument");
+  PB_REQUIRE(ctx->xchg_world > 0 && ctx->xchg_connected, "exchange not initialised / connected");
+  if (!ctx->xchg_pending) {
+    int rc = pb_exchange(ctx);
+    if (rc != PB_OK) return rc;
+  }
+  const unsigned long long want = ctx->xchg_seq;
+  volatile unsigned long long* flag = ctx->xchg_host_flag;
+  const double t0 = now_s();
+  unsigned long long spins = 0;
+  for (;;) {
+    const unsigned long long v = *flag;
+    if (v == want) break;
+    if (v == PB_XCHG_ERROR_FLAG) {
+      ctx->xchg_pending = 0;
+      pb_set_error("pb_exchange_wait: a peer did not publish sequence %llu within the device time-out", want);
+      return PB_ECUDA;
+    }
+    if ((++spins & 0x3ff) == 0) {
+      if (cudaStreamQuery(ctx->stream) == cudaSuccess && *flag != want) {
+        // the kernel that should have published has finished without doing so
+        if (*flag == want) break;
+        ctx->xchg_pending = 0;
+        pb_set_error("pb_exchange_wait: stream idle but sequence %llu never arrived (flag = %llu)", want, (unsigned long long)*flag);
+        return PB_ECUDA;
+      }
+      if (now_s() - t0 > timeout_s) {
+        ctx->xchg_pending = 0;
+        pb_set_error("pb_exchange_wait: timed out after %.1f s waiting for sequence %llu", timeout_s, want);
+        return PB_ECUDA;
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  __sync_synchronize();
+  memcpy(rows_out, ctx->xchg_host_rows, (size_t)ctx->xchg_world * PB_NSCALARS * sizeof(double));
+  ctx->xchg_pending = 0;
+  return PB_OK;
+}

@@ -139,6 +139,59 @@ class TorchDistComm:
         return out
 
 
+class DeviceExchangeComm:
+    """C1 done by the GPU (csrc/xchg.cuh): the last CTA of the fused step pushes this rank's scalar block to every peer
+    over NVLink (cudaIpc-mapped buffers), waits for the peers' blocks and drops all rows into mapped pinned host memory;
+    `exchange` only polls a pinned flag.  No collective launch, no cudaMemcpy, no stream synchronisation per iteration.
+    torch.distributed is used once, to all-gather the 64-byte IPC handles.  World size 1 = zero-copy read-back."""
+
+    def __init__(self, ctx, group=None, fused=True):
+        t = torch()
+        self.group = group
+        self.dist = None
+        self.rank, self.size = 0, 1
+        if t.distributed.is_available() and t.distributed.is_initialized():
+            self.dist = t.distributed
+            self.rank = self.dist.get_rank(group)
+            self.size = self.dist.get_world_size(group)
+        if self.size > L.PB_MAX_WORLD:
+            raise ValueError(f"DeviceExchangeComm supports at most {L.PB_MAX_WORLD} ranks")
+        if getattr(ctx, "_xchg_comm", None) is not None:
+            raise L.ProxB200Error("this context already owns a device exchange")
+        handle = C.create_string_buffer(L.PB_IPC_HANDLE_BYTES)
+        L.check(ctx.lib.pb_xchg_init(ctx.h, self.rank, self.size, handle))
+        if self.size > 1:
+            handles = [None] * self.size
+            self.dist.all_gather_object(handles, handle.raw, group=group)
+            blob = b"".join(handles)
+            L.check(ctx.lib.pb_xchg_connect(ctx.h, C.c_char_p(blob)))
+            self.dist.barrier(group=group)
+        L.check(ctx.lib.pb_ctx_set_option(ctx.h, L.PB_OPT_FUSED_EXCHANGE, 1 if fused else 0))
+        self._rows = (C.c_double * (self.size * L.PB_NSCALARS))()
+        self.ctx = ctx
+        ctx._xchg_comm = self
+        self.timeout_s = 20.0
+
+    def exchange(self, ctx) -> Scalars:
+        L.check(ctx.lib.pb_exchange_wait(ctx.h, self._rows, self.timeout_s))
+        return Scalars(np.frombuffer(self._rows, dtype=np.float64).reshape(self.size, L.PB_NSCALARS).copy())
+
+    def allgather_vector(self, v):
+        if self.size == 1:
+            return v[None, :]
+        t = torch()
+        out = t.empty((self.size, v.numel()), dtype=v.dtype, device=v.device)
+        self.dist.all_gather_into_tensor(out.view(-1), v.contiguous(), group=self.group)
+        return out
+
+    def close(self):
+        if self.ctx is not None:
+            L.check(self.ctx.lib.pb_ctx_set_option(self.ctx.h, L.PB_OPT_FUSED_EXCHANGE, 0))
+            L.check(self.ctx.lib.pb_xchg_shutdown(self.ctx.h))
+            self.ctx._xchg_comm = None
+            self.ctx = None
+
+
 def shard_bounds(n: int, size: int, align: int = 32):
     """Contiguous, `align`-element aligned index ranges of an n-vector over `size` ranks (last shard takes the remainder).
     align=32 keeps every fp32 shard 128-byte aligned; NormL21 callers pass a multiple of the group length."""

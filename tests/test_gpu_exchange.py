@@ -1,0 +1,135 @@
+"""C1 on the device (csrc/xchg.cuh): the in-kernel exchange delivers exactly the scalar block that the memcpy path reads,
+a solve driven by it takes the same iterations, and (on a box with >= 2 GPUs) a 2-rank row-sharded solve reproduces the
+single-GPU run bit for bit."""
+import ctypes as C
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import proxb200 as pa  # noqa: E402
+from oracle import fb_oracle as o  # noqa: E402
+from proxb200 import _lib as L  # noqa: E402
+from proxb200.host import Context, DeviceExchangeComm, ptr  # noqa: E402
+
+from conftest import ROOT, load_golden  # noqa: E402
+
+
+def test_device_exchange_world1_matches_memcpy_readback():
+    ctx = Context.get()
+    comm = DeviceExchangeComm(ctx)
+    try:
+        rng = np.random.default_rng(0)
+        n = 1_000_003
+        x, g, zp = (torch.as_tensor(rng.standard_normal(n).astype(np.float32)).cuda() for _ in range(3))
+        z, xn = torch.empty_like(x), torch.empty_like(x)
+        desc = L.pb_prox(L.PB_PROX_L1, 0, 0.7, 0.0, None, None)
+        for k in range(5):
+            L.check(ctx.lib.pb_ffb_step(ctx.h, L.PB_F32, n, ptr(x), ptr(g), ptr(zp), 0.1 + 0.01 * k, 0.5, C.byref(desc), None, ptr(z), None, ptr(xn)))
+            sc = comm.exchange(ctx)                       # fused: pushed by the step kernel's last CTA
+            row = ctx.read_scalars()                      # reference path: cudaMemcpy of the device block
+            assert sc.parts.shape == (1, L.PB_NSCALARS)
+            assert np.array_equal(sc.parts[0], row)
+        # a read that does not follow a fused step launches the stand-alone exchange kernel
+        L.check(ctx.lib.pb_nrm2sq(ctx.h, L.PB_F32, n, ptr(x)))
+        sc = comm.exchange(ctx)
+        assert np.array_equal(sc.parts[0], ctx.read_scalars())
+        # whole solves through the exchange: same iteration counts as the default path / the oracle
+        d = load_golden("lasso_small")
+        for alg, want in (("ffb", 788), ("fb", 1251)):
+            solver = (pa.FastForwardBackward if alg == "ffb" else pa.ForwardBackward)(tol=1e-6)
+            zsol, it = solver(x0=np.zeros(100), f=pa.LeastSquares(d["A"], d["b"]), g=pa.NormL1(float(d["lam"])), comm=comm)
+            assert it == want
+        zsol2, it2 = pa.FastForwardBackward(tol=1e-6)(x0=np.zeros(100), f=pa.LeastSquares(d["A"], d["b"]), g=pa.NormL1(float(d["lam"])))
+        zsol1, it1 = pa.FastForwardBackward(tol=1e-6)(x0=np.zeros(100), f=pa.LeastSquares(d["A"], d["b"]), g=pa.NormL1(float(d["lam"])), comm=comm)
+        assert it1 == it2 and np.array_equal(zsol1, zsol2)
+    finally:
+        comm.close()
+    # after close the context is back on the memcpy path
+    assert ctx.lib.pb_exchange(ctx.h) == 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, exchange, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import proxb200 as pa_
+        from proxb200.host import Context as Ctx, DeviceExchangeComm as DX, TorchDistComm, shard_bounds
+
+        ctx = Ctx.get()
+        comm = DX(ctx) if exchange == "device" else TorchDistComm()
+        rng = np.random.default_rng(7)
+        nblk, mb, nb = 8, 16, 64
+        blocks = rng.standard_normal((nblk, mb, nb)) / np.sqrt(mb)
+        b = rng.standard_normal(nblk * mb)
+        lam = 0.1 * np.max(np.abs(np.einsum("bij,bi->bj", blocks, b.reshape(nblk, mb))))
+        per = nblk // world
+        sl_b = slice(rank * per, (rank + 1) * per)
+        f = pa_.BlockDiagLeastSquares.from_numpy(blocks[sl_b], b[rank * per * mb:(rank + 1) * per * mb], comm=comm)
+        n = nblk * nb
+        x0 = np.zeros(per * nb)
+        out = {}
+        for name, kw in (("ffb_adaptive", {}), ("fb_adaptive", {}), ("ffb_fixed", dict(Lf=4.0))):
+            mk = pa_.ForwardBackward if name.startswith("fb") else pa_.FastForwardBackward
+            z, it = mk(tol=1e-7, maxit=5000)(x0=x0, f=f, g=pa_.NormL1(lam), comm=comm, n_global=n, **kw)
+            out[name] = (it, z)
+        q.put((rank, out))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("exchange", ["device", "nccl"])
+def test_two_rank_sharded_solve_equals_single_gpu(exchange):
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctxmp = mp.get_context("spawn")
+    q = ctxmp.Queue()
+    port = _free_port()
+    procs = [ctxmp.Process(target=_worker, args=(r, world, port, exchange, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # single-GPU run of the same problem in this process
+    rng = np.random.default_rng(7)
+    nblk, mb, nb = 8, 16, 64
+    blocks = rng.standard_normal((nblk, mb, nb)) / np.sqrt(mb)
+    b = rng.standard_normal(nblk * mb)
+    lam = 0.1 * np.max(np.abs(np.einsum("bij,bi->bj", blocks, b.reshape(nblk, mb))))
+    f = pa.BlockDiagLeastSquares.from_numpy(blocks, b)
+    fo = o.BlockDiagLeastSquares(blocks, b)
+    for name, kw in (("ffb_adaptive", {}), ("fb_adaptive", {}), ("ffb_fixed", dict(Lf=4.0))):
+        mk = pa.ForwardBackward if name.startswith("fb") else pa.FastForwardBackward
+        z1, it1 = mk(tol=1e-7, maxit=5000)(x0=np.zeros(nblk * nb), f=f, g=pa.NormL1(lam), **kw)
+        z2 = np.concatenate([res[r][name][1] for r in range(world)])
+        assert res[0][name][0] == res[1][name][0] == it1          # same iteration count on every rank and as 1 GPU
+        assert np.array_equal(z2, z1)                              # and the same bits
+        mk_o = o.forward_backward if name.startswith("fb") else o.fast_forward_backward
+        z_o, it_o = mk_o(np.zeros(nblk * nb), fo, o.NormL1(lam), tol=1e-7, maxit=5000, **kw)
+        assert abs(it1 - it_o) <= max(2, it_o // 100) and np.max(np.abs(z1 - z_o)) <= 1e-8
