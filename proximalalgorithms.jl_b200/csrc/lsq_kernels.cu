@@ -176,17 +176,15 @@ static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
     return pb_nrm2sq(ctx, sizeof(T) == 4 ? PB_F32 : PB_F64, 0, nullptr);
   }
   const int64_t row_tiles = (mb + GEMV_ROWS - 1) / GEMV_ROWS;
-  // enough CTAs to cover the machine ~4x, but at least GEMV_CL*GEMV_UNROLL columns per chunk
-  int64_t target = (int64_t)ctx->sm_count * 4;
-  int64_t nchunk = target / (row_tiles * nblk);
-  if (nchunk < 1) nchunk = 1;
-  int64_t min_cols = GEMV_CL * GEMV_UNROLL;
-  if (nchunk > (nb + min_cols - 1) / min_cols) nchunk = (nb + min_cols - 1) / min_cols;
-  if (nchunk < 1) nchunk = 1;
-  if (nchunk > 65535) nchunk = 65535;
-  int64_t chunk_cols = (nb + nchunk - 1) / nchunk;
-  if (chunk_cols < 1) chunk_cols = 1;
-  nchunk = nb > 0 ? (nb + chunk_cols - 1) / chunk_cols : 1;
+  // Column chunking is a function of the BLOCK SHAPE ONLY (never of nblk or the SM count): the summation order of every
+  // r_i is then the same on any GPU and for any sharding of the blocks over ranks, so a block-sharded run reproduces the
+  // single-GPU bits.  ceil(nb/64) columns per chunk, clamped to [32, 4096]  ->  <= 64 chunks (more only for nb > 262144).
+  int64_t chunk_cols = (nb + 63) / 64;
+  if (chunk_cols < GEMV_CL * GEMV_UNROLL) chunk_cols = GEMV_CL * GEMV_UNROLL;
+  if (chunk_cols > 4096) chunk_cols = 4096;
+  int64_t nchunk = nb > 0 ? (nb + chunk_cols - 1) / chunk_cols : 1;
+  PB_REQUIRE(nchunk <= 65535, "too many column chunks for one launch");
+  (void)row_tiles;
   PB_REQUIRE(nblk <= 65535, "too many blocks for one launch (nblk <= 65535)");
   int rc = pb_ensure_scratch(ctx, (size_t)nchunk * M * sizeof(T));
   if (rc != PB_OK) return rc;

@@ -213,3 +213,56 @@ def test_verbose_display_and_maxit(capsys):
     z, it = solver(x0=np.zeros(10), f=pa.LeastSquares(d["A"], d["b"]), g=pa.NormL1(d["lam"]))
     out = capsys.readouterr().out.strip().splitlines()
     assert it == 50 and len(out) == 5 and out[0].split("|")[0].strip() == "10"
+
+
+def _m1_problem():
+    """SURVEY.md section 8d M1 = BASELINE.json configs[0] as written: synthetic 200 x 500 fp64 Lasso, seed 1."""
+    rng = np.random.default_rng(1)
+    A = np.asfortranarray(rng.standard_normal((200, 500)))
+    xt = np.zeros(500)
+    idx = rng.choice(500, 25, replace=False)
+    xt[idx] = rng.standard_normal(25)
+    b = A @ xt + 0.01 * rng.standard_normal(200)
+    lam = 0.1 * np.max(np.abs(A.T @ b))
+    return A, b, lam
+
+
+@pytest.mark.parametrize("alg", ["ffb", "fb"])
+@pytest.mark.parametrize("mode", ["adaptive", "fixed"])
+def test_config1_synthetic_200x500(alg, mode):
+    A, b, lam = _m1_problem()
+    kw = {} if mode == "adaptive" else dict(Lf=np.linalg.norm(A, 2) ** 2)
+    so = o.fast_forward_backward if alg == "ffb" else o.forward_backward
+    z_o, it_o = so(np.zeros(500), o.LeastSquares(A, b), o.NormL1(lam), tol=1e-6, **kw)
+    sg = (pa.FastForwardBackward if alg == "ffb" else pa.ForwardBackward)(tol=1e-6)
+    z, it = sg(x0=np.zeros(500), f=pa.LeastSquares(A, b), g=pa.NormL1(lam), **kw)
+    assert it == it_o and it < 10000
+    assert np.max(np.abs(z - z_o)) <= 1e-9 * max(1.0, np.max(np.abs(z_o)))
+    assert abs(_objective(A, b, lam, z) - _objective(A, b, lam, z_o)) / _objective(A, b, lam, z_o) <= 1e-10
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_config2_blockdiag_lasso_fista(T):
+    """BASELINE.json configs[1] structure (block-diagonal implicit A, FISTA + NormL1, fixed gamma = 1/L from 20 power
+    iterations) at a size the oracle finishes in seconds."""
+    rng = np.random.default_rng(2)
+    nblk, mb, nb = 6, 20, 400
+    blocks = (rng.standard_normal((nblk, mb, nb)) / np.sqrt(mb)).astype(T)
+    xt = np.zeros(nblk * nb)
+    idx = rng.choice(nblk * nb, 24, replace=False)
+    xt[idx] = rng.standard_normal(24)
+    b = (np.einsum("bij,bj->bi", blocks.astype(np.float64), xt.reshape(nblk, nb)).reshape(-1) + 0.01 * rng.standard_normal(nblk * mb)).astype(T)
+    lam = T(0.1 * np.max(np.abs(np.einsum("bij,bi->bj", blocks.astype(np.float64), b.reshape(nblk, mb).astype(np.float64)))))
+    v = rng.standard_normal(nblk * nb)
+    for _ in range(20):
+        w = np.einsum("bij,bi->bj", blocks.astype(np.float64), np.einsum("bij,bj->bi", blocks.astype(np.float64), v.reshape(nblk, nb))).reshape(-1)
+        Lhat = np.linalg.norm(w) / np.linalg.norm(v)
+        v = w / np.linalg.norm(w)
+    Lf = T(1.05 * Lhat)
+    tol = T(1e-6 if T == np.float64 else 1e-4)
+    z_o, it_o = o.fast_forward_backward(np.zeros(nblk * nb, T), o.BlockDiagLeastSquares(blocks, b), o.NormL1(lam), tol=tol, Lf=Lf)
+    z, it = pa.FastForwardBackward(tol=tol)(x0=np.zeros(nblk * nb, T), f=pa.BlockDiagLeastSquares.from_numpy(blocks, b), g=pa.NormL1(lam), Lf=Lf)
+    if T == np.float64:
+        assert it == it_o and np.max(np.abs(z - z_o)) <= 1e-9
+    else:
+        assert abs(it - it_o) <= max(2, it_o // 100) and np.max(np.abs(z - z_o)) <= 1e-4
