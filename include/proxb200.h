@@ -120,7 +120,7 @@ int64_t pb_ctx_launch_count(pb_ctx* ctx);
  * read-back.  Set-up: every rank calls pb_xchg_init (gets a PB_IPC_HANDLE_BYTES handle), the host framework all-gathers
  * the handles (any transport), every rank calls pb_xchg_connect.  All ranks must issue the same sequence of exchanges. */
 #define PB_IPC_HANDLE_BYTES 64
-#define PB_MAX_WORLD 16
+#define PB_MAX_WORLD 8
 int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out);
 int pb_xchg_connect(pb_ctx* ctx, const void* all_handles /* world x PB_IPC_HANDLE_BYTES, rank order */);
 int pb_xchg_shutdown(pb_ctx* ctx);

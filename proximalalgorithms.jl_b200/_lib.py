@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libproxb200.so")
 PB_F32, PB_F64 = 0, 1
 PB_PROX_ZERO, PB_PROX_L1, PB_PROX_BOX, PB_PROX_SCALE, PB_PROX_L21 = 0, 1, 2, 3, 4
 PB_OPT_CTAS_PER_SM, PB_OPT_STREAM_HINTS, PB_OPT_UNROLL, PB_OPT_STEP_IMPL, PB_OPT_FUSED_EXCHANGE = 0, 1, 2, 3, 4
-PB_IPC_HANDLE_BYTES, PB_MAX_WORLD = 64, 16
+PB_IPC_HANDLE_BYTES, PB_MAX_WORLD = 64, 8
 PB_S_GSUM, PB_S_RESSQ, PB_S_GDR, PB_S_RESINF, PB_S_AUX, PB_S_AUXINF, PB_NSCALARS = 0, 2, 4, 6, 8, 10, 16
 
 

@@ -46,17 +46,15 @@ struct pb_ctx {
   void* hbuf[5];
   size_t hbuf_bytes;
   // C1 exchange (xchg.cu): own IPC-exported buffer, peer mappings, mapped pinned landing zone for the host
-  double* xchg_own;
-  double* xchg_peer[PB_MAX_RANKS];
-  double* xchg_host_rows;               // host pointer (pinned, mapped)
-  double* xchg_host_rows_dev;           // its device alias
-  unsigned long long* xchg_host_flag;   // host pointer
-  unsigned long long* xchg_host_flag_dev;
-  unsigned long long xchg_seq;          // last sequence number issued
-  int xchg_rank, xchg_world;            // world == 0: not initialised
+  unsigned long long* xchg_own;
+  unsigned long long* xchg_peer[PB_MAX_RANKS];
+  unsigned long long* xchg_host_words;      // host pointer (pinned, mapped): [world][32] words
+  unsigned long long* xchg_host_words_dev;  // its device alias
+  unsigned int xchg_seq;                    // last sequence number issued
+  int xchg_rank, xchg_world;                // world == 0: not initialised
   int xchg_connected;
-  int xchg_fused;                       // K1/K2 push in-kernel
-  int xchg_pending;                     // a launched kernel will publish xchg_seq
+  int xchg_fused;                           // K1/K2 push in-kernel
+  int xchg_pending;                         // a launched kernel will publish xchg_seq
 };
 
 // Fill the kernel-side parameters for the next in-kernel exchange (advances the sequence number); world = 0 if disabled.

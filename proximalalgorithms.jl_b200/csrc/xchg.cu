@@ -1,11 +1,13 @@
 // xchg.cu -- host side of C1 (see xchg.cuh): IPC set-up of the per-rank exchange buffers, the stand-alone 1-CTA exchange
-// kernel for reads that do not follow a fused step, and the host-side wait on the mapped pinned flag.
+// kernel for reads that do not follow a fused step, and the host-side wait on the mapped pinned words.
 #include <string.h>
 #include <time.h>
 
 #include "common.cuh"
 
 static_assert(sizeof(cudaIpcMemHandle_t) == PB_IPC_HANDLE_BYTES, "PB_IPC_HANDLE_BYTES must match cudaIpcMemHandle_t");
+static_assert(PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW <= PB_BLOCK, "one thread per word");
+static_assert(PB_MAX_WORLD == PB_MAX_RANKS, "header and implementation disagree on the maximum world size");
 
 __global__ void __launch_bounds__(PB_BLOCK) k_xchg(XchgParams xp, const double* local_block) {
   xchg_push_wait(xp, local_block);
@@ -15,10 +17,10 @@ void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want) {
   memset(xp, 0, sizeof(*xp));
   if (!want || ctx->xchg_world <= 0 || !ctx->xchg_connected) return;
   ctx->xchg_seq += 1;
+  if (ctx->xchg_seq == 0 || ctx->xchg_seq == PB_XCHG_ERROR_SEQ) ctx->xchg_seq = 1;   // both values are reserved
   ctx->xchg_pending = 1;
   for (int r = 0; r < ctx->xchg_world; ++r) xp->peer[r] = ctx->xchg_peer[r];
-  xp->host_rows = ctx->xchg_host_rows_dev;
-  xp->host_flag = ctx->xchg_host_flag_dev;
+  xp->host_words = ctx->xchg_host_words_dev;
   xp->seq = ctx->xchg_seq;
   xp->rank = ctx->xchg_rank;
   xp->world = ctx->xchg_world;
@@ -26,20 +28,21 @@ void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want) {
 
 extern "C" int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out) {
   PB_REQUIRE(ctx != nullptr, "null context");
-  PB_REQUIRE(world >= 1 && world <= PB_MAX_RANKS && rank >= 0 && rank < world, "need 0 <= rank < world <= 16");
+  PB_REQUIRE(world >= 1 && world <= PB_MAX_RANKS && rank >= 0 && rank < world, "need 0 <= rank < world <= 8");
   PB_REQUIRE(ctx->xchg_world == 0, "exchange already initialised on this context");
   PB_CHECK_CUDA(cudaSetDevice(ctx->device));
-  PB_CHECK_CUDA(cudaMalloc(&ctx->xchg_own, PB_XCHG_BYTES));
-  PB_CHECK_CUDA(cudaMemset(ctx->xchg_own, 0, PB_XCHG_BYTES));
+  void* own = nullptr;
+  PB_CHECK_CUDA(cudaMalloc(&own, PB_XCHG_BYTES));
+  PB_CHECK_CUDA(cudaMemset(own, 0, PB_XCHG_BYTES));
+  ctx->xchg_own = static_cast<unsigned long long*>(own);
   void* host = nullptr;
-  PB_CHECK_CUDA(cudaHostAlloc(&host, (size_t)PB_MAX_RANKS * PB_NSCALARS * 8 + 64, cudaHostAllocMapped | cudaHostAllocPortable));
-  memset(host, 0, (size_t)PB_MAX_RANKS * PB_NSCALARS * 8 + 64);
-  ctx->xchg_host_rows = static_cast<double*>(host);
-  ctx->xchg_host_flag = reinterpret_cast<unsigned long long*>(ctx->xchg_host_rows + PB_MAX_RANKS * PB_NSCALARS);
+  const size_t hbytes = (size_t)PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW * 8;
+  PB_CHECK_CUDA(cudaHostAlloc(&host, hbytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(host, 0, hbytes);
+  ctx->xchg_host_words = static_cast<unsigned long long*>(host);
   void* dev_alias = nullptr;
   PB_CHECK_CUDA(cudaHostGetDevicePointer(&dev_alias, host, 0));
-  ctx->xchg_host_rows_dev = static_cast<double*>(dev_alias);
-  ctx->xchg_host_flag_dev = reinterpret_cast<unsigned long long*>(ctx->xchg_host_rows_dev + PB_MAX_RANKS * PB_NSCALARS);
+  ctx->xchg_host_words_dev = static_cast<unsigned long long*>(dev_alias);
   ctx->xchg_rank = rank;
   ctx->xchg_world = world;
   ctx->xchg_seq = 0;
@@ -50,11 +53,8 @@ extern "C" int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out) 
   if (world == 1) ctx->xchg_connected = 1;
   if (handle_out) {
     cudaIpcMemHandle_t h;
-    if (world > 1) {
-      PB_CHECK_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg_own));
-    } else {
-      memset(&h, 0, sizeof(h));
-    }
+    memset(&h, 0, sizeof(h));
+    if (world > 1) PB_CHECK_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg_own));
     memcpy(handle_out, &h, sizeof(h));
   }
   PB_CHECK_CUDA(cudaDeviceSynchronize());
@@ -73,7 +73,7 @@ extern "C" int pb_xchg_connect(pb_ctx* ctx, const void* all_handles) {
     memcpy(&h, hs + (size_t)r * PB_IPC_HANDLE_BYTES, sizeof(h));
     void* p = nullptr;
     PB_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    ctx->xchg_peer[r] = static_cast<double*>(p);
+    ctx->xchg_peer[r] = static_cast<unsigned long long*>(p);
   }
   ctx->xchg_connected = 1;
   return PB_OK;
@@ -86,12 +86,13 @@ extern "C" int pb_xchg_shutdown(pb_ctx* ctx) {
   for (int r = 0; r < ctx->xchg_world; ++r)
     if (r != ctx->xchg_rank && ctx->xchg_peer[r]) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
   if (ctx->xchg_own) cudaFree(ctx->xchg_own);
-  if (ctx->xchg_host_rows) cudaFreeHost(ctx->xchg_host_rows);
+  if (ctx->xchg_host_words) cudaFreeHost(ctx->xchg_host_words);
   ctx->xchg_own = nullptr;
-  ctx->xchg_host_rows = nullptr;
+  ctx->xchg_host_words = nullptr;
   ctx->xchg_world = 0;
   ctx->xchg_connected = 0;
   ctx->xchg_fused = 0;
+  ctx->xchg_pending = 0;
   return PB_OK;
 }
 
@@ -120,38 +121,39 @@ extern "C" int pb_exchange_wait(pb_ctx* ctx, double* rows_out, double timeout_s)
     int rc = pb_exchange(ctx);
     if (rc != PB_OK) return rc;
   }
-  const unsigned long long want = ctx->xchg_seq;
-  volatile unsigned long long* flag = ctx->xchg_host_flag;
+  const unsigned int want = ctx->xchg_seq;
+  const int nwords = ctx->xchg_world * PB_XCHG_WORDS_PER_ROW;
+  volatile unsigned long long* words = ctx->xchg_host_words;
+  unsigned long long got[PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW];
   const double t0 = now_s();
   unsigned long long spins = 0;
-  for (;;) {
-    const unsigned long long v = *flag;
-    if (v == want) break;
-    if (v == PB_XCHG_ERROR_FLAG) {
+  int i = nwords - 1;   // scan backwards: the words usually land in ascending order, so the last one arrives last
+  while (i >= 0) {
+    const unsigned long long v = words[i];
+    const unsigned int s = (unsigned int)(v >> 32);
+    if (s == want) {
+      got[i] = v;
+      --i;
+      continue;
+    }
+    if (s == PB_XCHG_ERROR_SEQ) {
       ctx->xchg_pending = 0;
-      pb_set_error("pb_exchange_wait: a peer did not publish sequence %llu within the device time-out", want);
+      pb_set_error("pb_exchange_wait: a peer did not publish sequence %u within the device time-out", want);
       return PB_ECUDA;
     }
-    if ((++spins & 0x3ff) == 0) {
-      if (cudaStreamQuery(ctx->stream) == cudaSuccess && *flag != want) {
-        // the kernel that should have published has finished without doing so
-        if (*flag == want) break;
-        ctx->xchg_pending = 0;
-        pb_set_error("pb_exchange_wait: stream idle but sequence %llu never arrived (flag = %llu)", want, (unsigned long long)*flag);
-        return PB_ECUDA;
-      }
-      if (now_s() - t0 > timeout_s) {
-        ctx->xchg_pending = 0;
-        pb_set_error("pb_exchange_wait: timed out after %.1f s waiting for sequence %llu", timeout_s, want);
-        return PB_ECUDA;
-      }
+    if ((++spins & 0xfff) == 0 && now_s() - t0 > timeout_s) {
+      ctx->xchg_pending = 0;
+      pb_set_error("pb_exchange_wait: timed out after %.1f s waiting for sequence %u (word %d)", timeout_s, want, i);
+      return PB_ECUDA;
     }
 #if defined(__x86_64__)
     __builtin_ia32_pause();
 #endif
   }
-  __sync_synchronize();
-  memcpy(rows_out, ctx->xchg_host_rows, (size_t)ctx->xchg_world * PB_NSCALARS * sizeof(double));
+  for (int k = 0; k < ctx->xchg_world * PB_NSCALARS; ++k) {
+    const unsigned long long bits = (got[2 * k] & 0xffffffffull) | ((got[2 * k + 1] & 0xffffffffull) << 32);
+    memcpy(&rows_out[k], &bits, 8);
+  }
   ctx->xchg_pending = 0;
   return PB_OK;
 }

@@ -2,88 +2,76 @@
 //
 // Every rank owns an exchange buffer in device memory (cudaMalloc, exported with cudaIpc and mapped by all peers over
 // NVLink).  The last CTA of a reducing kernel (or the 1-CTA k_xchg kernel) pushes this rank's PB_NSCALARS doubles into
-// slot [parity][rank] of EVERY rank's buffer with plain peer stores, publishes a sequence number with a system-scope
-// release, waits until all P sequence numbers of its own buffer have arrived, and copies the P rows into mapped pinned
-// host memory followed by a host-visible flag.  The host then needs neither a collective launch nor a cudaMemcpy nor a
-// stream synchronisation: it polls the pinned flag (pb_exchange_wait) and folds the rows in rank order in double-double.
-// With one rank this degenerates to a zero-copy read-back of the scalar block.
+// slot [parity][rank] of EVERY rank's buffer with plain peer stores, waits until the P rows of its own buffer have
+// arrived and forwards them to mapped pinned host memory, where the host polls for them (pb_exchange_wait).  The host
+// needs neither a collective launch nor a cudaMemcpy nor a stream synchronisation, and folds the rows in rank order in
+// double-double.  With one rank this degenerates to a zero-copy read-back of the scalar block.
+//
+// Wire format ("LL" style, as NCCL's low-latency protocol): every double travels as two 8-byte words {32 data bits,
+// 32-bit sequence number}.  An aligned 8-byte store is atomic on NVLink and on PCIe, so a consumer that sees the expected
+// sequence number in a word also sees its data bits -- no fences, no separate flags, and no reliance on the ORDER in
+// which posted writes become visible (a flag-after-data protocol over PCIe was observed to hand stale rows to the host
+// occasionally).
 //
 // Double buffering by the parity of the sequence number is sufficient: a rank can only complete exchange k+1 after every
-// peer has pushed k+1, which a peer does after its own exchange-k kernel (same stream) has finished reading parity k.
+// peer has pushed k+1, which a peer does in its kernel k+1, i.e. after its kernel k (same stream) finished reading parity k.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "proxb200.h"
 
-#define PB_MAX_RANKS 16
-#define PB_XCHG_BLOCK_DOUBLES (2 * PB_MAX_RANKS * PB_NSCALARS)                 // blocks[2][MAXR][16]
-#define PB_XCHG_BYTES (PB_XCHG_BLOCK_DOUBLES * 8 + 2 * PB_MAX_RANKS * 8)       // + flags[2][MAXR] (u64)
-#define PB_XCHG_TIMEOUT_NS 4000000000ull                                       // give up after 4 s (never hang the GPU)
-#define PB_XCHG_ERROR_FLAG 0xFFFFFFFFFFFFFFFFull
+#define PB_MAX_RANKS 8                                    // one NVSwitch domain; PB_MAX_RANKS * 32 words <= 256 threads
+#define PB_XCHG_WORDS_PER_ROW (2 * PB_NSCALARS)           // 32 eight-byte words per row
+#define PB_XCHG_WORDS (2 * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW)   // [parity][rank][word]
+#define PB_XCHG_BYTES (PB_XCHG_WORDS * 8)
+#define PB_XCHG_TIMEOUT_NS 4000000000ull                  // give up after 4 s (never hang the GPU)
+#define PB_XCHG_ERROR_SEQ 0xFFFFFFFFu
 
 struct XchgParams {
-  double* peer[PB_MAX_RANKS];        // peer[r]: base of rank r's exchange buffer as mapped in THIS process
-  double* host_rows;                 // device alias of mapped pinned memory: [world][PB_NSCALARS]
-  unsigned long long* host_flag;     // device alias of the mapped pinned sequence flag
-  unsigned long long seq;            // sequence number of this exchange (> 0)
-  int rank, world;                   // world == 0: exchange disabled
+  unsigned long long* peer[PB_MAX_RANKS];   // peer[r]: base of rank r's exchange buffer as mapped in THIS process
+  unsigned long long* host_words;           // device alias of mapped pinned memory: [world][32] words
+  unsigned int seq;                         // sequence number of this exchange (never 0, never PB_XCHG_ERROR_SEQ)
+  int rank, world;                          // world == 0: exchange disabled
 };
 
-__device__ __forceinline__ unsigned long long* xchg_flags(double* base) {
-  return reinterpret_cast<unsigned long long*>(base + PB_XCHG_BLOCK_DOUBLES);
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void st_word(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
-// Executed by ALL threads of one CTA (blockDim.x >= world * PB_NSCALARS) after `local_block` is final and visible to the
-// CTA.  Contains __syncthreads.
+// Executed by ALL threads of one CTA (blockDim.x >= world * 32) after `local_block` is final and visible to the CTA.
 __device__ __forceinline__ void xchg_push_wait(const XchgParams& xp, const double* local_block) {
   const int t = threadIdx.x;
-  const int par = (int)(xp.seq & 1ull);
-  const int nelem = xp.world * PB_NSCALARS;
-  __shared__ int timed_out;
-  if (t == 0) timed_out = 0;
-  // 1. push my row into slot [par][rank] of every rank's buffer (NVLink peer stores; self included)
-  if (t < nelem) {
-    const int r = t / PB_NSCALARS, i = t % PB_NSCALARS;
-    const double v = __ldcg(local_block + i);
-    double* dst = xp.peer[r] + ((size_t)(par * PB_MAX_RANKS + xp.rank) * PB_NSCALARS + i);
-    *reinterpret_cast<volatile double*>(dst) = v;
-    __threadfence_system();
-  }
-  __syncthreads();
-  // 2. publish the sequence number to every rank, 3. wait for everybody's number in my own buffer
-  if (t < xp.world) {
-    st_release_sys(xchg_flags(xp.peer[t]) + par * PB_MAX_RANKS + xp.rank, xp.seq);
-    const unsigned long long* mine = xchg_flags(xp.peer[xp.rank]) + par * PB_MAX_RANKS + t;
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(mine) != xp.seq) {
-      if (globaltimer_ns() - t0 > PB_XCHG_TIMEOUT_NS) {
-        timed_out = 1;
-        break;
-      }
-      __nanosleep(64);
+  const int par = (int)(xp.seq & 1u);
+  const int nwords = xp.world * PB_XCHG_WORDS_PER_ROW;
+  if (t >= nwords) return;
+  const int r = t / PB_XCHG_WORDS_PER_ROW, w = t % PB_XCHG_WORDS_PER_ROW;
+  // 1. push word w of my row into slot [par][rank] of rank r's buffer (NVLink peer store; self included)
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(local_block + (w >> 1)));
+  const unsigned int half = (w & 1) ? (unsigned int)(bits >> 32) : (unsigned int)(bits & 0xffffffffull);
+  st_word(xp.peer[r] + ((size_t)(par * PB_MAX_RANKS + xp.rank) * PB_XCHG_WORDS_PER_ROW + w),
+          ((unsigned long long)xp.seq << 32) | half);
+  // 2. wait for word w of rank r's row in MY buffer, 3. forward it to the host
+  const unsigned long long* mine = xp.peer[xp.rank] + ((size_t)(par * PB_MAX_RANKS + r) * PB_XCHG_WORDS_PER_ROW + w);
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned long long v = ld_word(mine);
+  while ((unsigned int)(v >> 32) != xp.seq) {
+    if (globaltimer_ns() - t0 > PB_XCHG_TIMEOUT_NS) {
+      v = ((unsigned long long)PB_XCHG_ERROR_SEQ << 32);
+      break;
     }
+    __nanosleep(32);
+    v = ld_word(mine);
   }
-  __syncthreads();
-  // 4. rows -> mapped pinned host memory, then the host-visible flag
-  if (t < nelem) {
-    const double v = __ldcg(xp.peer[xp.rank] + ((size_t)par * PB_MAX_RANKS * PB_NSCALARS + t));
-    *reinterpret_cast<volatile double*>(xp.host_rows + t) = v;
-    __threadfence_system();
-  }
-  __syncthreads();
-  if (t == 0) st_release_sys(xp.host_flag, timed_out ? PB_XCHG_ERROR_FLAG : xp.seq);
+  st_word(xp.host_words + t, v);
 }
