@@ -55,6 +55,7 @@ struct pb_ctx {
   int xchg_connected;
   int xchg_fused;                           // K1/K2 push in-kernel
   int xchg_pending;                         // a launched kernel will publish xchg_seq
+  int64_t xchg_pending_launch;              // value of `launches` right after that kernel's launch
 };
 
 // Fill the kernel-side parameters for the next in-kernel exchange (advances the sequence number); world = 0 if disabled.

@@ -19,6 +19,7 @@ void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want) {
   ctx->xchg_seq += 1;
   if (ctx->xchg_seq == 0 || ctx->xchg_seq == PB_XCHG_ERROR_SEQ) ctx->xchg_seq = 1;   // both values are reserved
   ctx->xchg_pending = 1;
+  ctx->xchg_pending_launch = ctx->launches + 1;   // the caller launches exactly one kernel next: the one that publishes
   for (int r = 0; r < ctx->xchg_world; ++r) xp->peer[r] = ctx->xchg_peer[r];
   xp->host_words = ctx->xchg_host_words_dev;
   xp->seq = ctx->xchg_seq;
@@ -117,7 +118,9 @@ static double now_s() {
 extern "C" int pb_exchange_wait(pb_ctx* ctx, double* rows_out, double timeout_s) {
   PB_REQUIRE(ctx != nullptr && rows_out != nullptr, "null argument");
   PB_REQUIRE(ctx->xchg_world > 0 && ctx->xchg_connected, "exchange not initialised / connected");
-  if (!ctx->xchg_pending) {
+  // An exchange is current only if its publishing kernel is the most recent launch of this context: if other kernels
+  // (which may have changed the scalar block) were enqueued since, or nothing is pending, publish the block afresh.
+  if (!ctx->xchg_pending || ctx->launches != ctx->xchg_pending_launch) {
     int rc = pb_exchange(ctx);
     if (rc != PB_OK) return rc;
   }
