@@ -160,6 +160,101 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step_l21(StepParams p, int group) 
   grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map, &p.xchg);
 }
 
+// NormL21 step, vectorised single pass: group = KP * 32 * VEC elements, one warp per group, each lane keeps its KP packs of
+// x, grad (and z_prev) in registers, so every vector is read exactly once (the generic kernel above re-reads x and grad
+// from L1 in its second sweep and uses scalar loads).
+template <typename T, bool EXTRAP, int KP>
+__global__ void __launch_bounds__(PB_BLOCK) k_step_l21_vec(StepParams p) {
+  constexpr bool COMP = sizeof(T) == 8;
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int GROUP = KP * 32 * VEC;
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  const T* __restrict__ g = static_cast<const T*>(p.grad);
+  const T* __restrict__ zp = static_cast<const T*>(p.z_prev);
+  T* __restrict__ yo = static_cast<T*>(p.y);
+  T* __restrict__ zo = static_cast<T*>(p.z);
+  T* __restrict__ ro = static_cast<T*>(p.res);
+  T* __restrict__ xo = static_cast<T*>(p.x_next);
+  const T gamma = (T)p.gamma, beta = (T)p.beta, gl = (T)p.a;
+  const int lane = threadIdx.x & 31;
+  const int64_t ngroups = p.n / GROUP;
+  const int64_t warp0 = ((int64_t)blockIdx.x * PB_BLOCK + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * PB_BLOCK) >> 5;
+  Acc<3, 1> acc;
+  acc.clear();
+  for (int64_t gi = warp0; gi < ngroups; gi += nwarps) {
+    const int64_t base = gi * GROUP + (int64_t)lane * VEC;
+    Pack<T, VEC> xv[KP], gv[KP], zv[KP], yv[KP];
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+      xv[q] = ld_pack<T, VEC, true>(x + base + q * 32 * VEC);
+      gv[q] = ld_pack<T, VEC, true>(g + base + q * 32 * VEC);
+      if constexpr (EXTRAP) zv[q] = ld_pack<T, VEC, true>(zp + base + q * 32 * VEC);
+    }
+    dd ss;
+    ss.hi = ss.lo = 0.0;
+#pragma unroll
+    for (int q = 0; q < KP; ++q)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        yv[q].v[e] = sub_rn(xv[q].v[e], mul_rn(gamma, gv[q].v[e]));
+        if (COMP)
+          dd_add_prod(ss, (double)yv[q].v[e], (double)yv[q].v[e]);
+        else
+          ss.hi = __fma_rn((double)yv[q].v[e], (double)yv[q].v[e], ss.hi);
+      }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      dd o;
+      o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
+      o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
+      ss = dd_sum(ss, o);
+    }
+    const T ns = (T)sqrt(ss.hi + ss.lo);
+    T scal = sub_rn(T(1), gl / ns);
+    scal = (scal <= T(0)) ? T(0) : scal;
+    if (lane == 0) {
+      const double contrib = (double)mul_rn(scal, ns);
+      if (COMP)
+        dd_add(acc.s[0], contrib);
+      else
+        acc.s[0].hi += contrib;
+    }
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+      Pack<T, VEC> zn, rv, xn;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        zn.v[e] = mul_rn(scal, yv[q].v[e]);
+        rv.v[e] = sub_rn(xv[q].v[e], zn.v[e]);
+        if constexpr (EXTRAP) xn.v[e] = add_rn(zn.v[e], mul_rn(beta, sub_rn(zn.v[e], zv[q].v[e])));
+        const double rd = (double)rv.v[e], gd = (double)gv[q].v[e];
+        if (COMP) {
+          dd_add_prod(acc.s[1], rd, rd);
+          dd_add_prod(acc.s[2], gd, rd);
+        } else {
+          acc.s[1].hi = __fma_rn(rd, rd, acc.s[1].hi);
+          acc.s[2].hi = __fma_rn(gd, rd, acc.s[2].hi);
+        }
+        acc.m[0] = nanmax(acc.m[0], fabs(rd));
+      }
+      const int64_t i = base + q * 32 * VEC;
+      st_pack<T, VEC, true>(zo + i, zn);
+      if constexpr (EXTRAP) st_pack<T, VEC, true>(xo + i, xn);
+      if (yo) st_pack<T, VEC, true>(yo + i, yv[q]);
+      if (ro) st_pack<T, VEC, true>(ro + i, rv);
+    }
+  }
+  OutMap map;
+  map.sum_slot[0] = PB_S_GSUM;
+  map.sum_slot[1] = PB_S_RESSQ;
+  map.sum_slot[2] = PB_S_GDR;
+  map.sum_slot[3] = -1;
+  map.max_slot[0] = PB_S_RESINF;
+  map.max_slot[1] = -1;
+  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map, &p.xchg);
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // generic element-wise kernel with up to three inputs, one output and one sum / one max reduction (K3, K6)
 // ----------------------------------------------------------------------------------------------------------------
@@ -470,7 +565,16 @@ static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool ve
     PB_REQUIRE(g->group > 0 && p.n % g->group == 0, "NormL21 group must divide n");
     const int64_t ngroups = p.n / g->group;
     const int grid = pb_stream_grid(ctx, PB_BLOCK / 32, ngroups, 8);
-    k_step_l21<T, EXTRAP><<<grid, PB_BLOCK, 0, ctx->stream>>>(p, g->group);
+    constexpr int VEC = 16 / sizeof(T);
+    const int kp = (g->group % (32 * VEC) == 0) ? g->group / (32 * VEC) : 0;
+    if (vec_ok && kp == 1)
+      k_step_l21_vec<T, EXTRAP, 1><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+    else if (vec_ok && kp == 2)
+      k_step_l21_vec<T, EXTRAP, 2><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+    else if (vec_ok && kp == 4)
+      k_step_l21_vec<T, EXTRAP, 4><<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
+    else
+      k_step_l21<T, EXTRAP><<<grid, PB_BLOCK, 0, ctx->stream>>>(p, g->group);
     PB_LAUNCH_CHECK(ctx);
     return PB_OK;
   }

@@ -126,7 +126,7 @@ def test_box_with_per_element_bounds_and_nan_inf(T):
 
 
 @pytest.mark.parametrize("T", TYPES)
-@pytest.mark.parametrize("group,ngroups", [(128, 1000), (128, 1), (4, 33), (100, 77), (1, 50), (513, 9)])
+@pytest.mark.parametrize("group,ngroups", [(128, 1000), (128, 1), (4, 33), (100, 77), (1, 50), (513, 9), (256, 37), (512, 11), (64, 40)])
 def test_l21_step_matches_oracle(T, group, ngroups):
     n = group * ngroups
     x, g, zp = _inputs(T, n, seed=11)
