@@ -182,15 +182,29 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step_l21_vec(StepParams p) {
   const int64_t nwarps = ((int64_t)gridDim.x * PB_BLOCK) >> 5;
   Acc<3, 1> acc;
   acc.clear();
+  // software pipeline: the loads of the warp's NEXT group are issued before the current group is reduced, so the
+  // shuffle / sqrt / divide latency chain of one group overlaps the memory latency of the next
+  Pack<T, VEC> nx[KP], ng[KP], nz[KP];
+  auto load_group = [&](int64_t gi_) {
+    const int64_t b_ = gi_ * GROUP + (int64_t)lane * VEC;
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+      nx[q] = ld_pack<T, VEC, true>(x + b_ + q * 32 * VEC);
+      ng[q] = ld_pack<T, VEC, true>(g + b_ + q * 32 * VEC);
+      if constexpr (EXTRAP) nz[q] = ld_pack<T, VEC, true>(zp + b_ + q * 32 * VEC);
+    }
+  };
+  if (warp0 < ngroups) load_group(warp0);
   for (int64_t gi = warp0; gi < ngroups; gi += nwarps) {
     const int64_t base = gi * GROUP + (int64_t)lane * VEC;
     Pack<T, VEC> xv[KP], gv[KP], zv[KP], yv[KP];
 #pragma unroll
     for (int q = 0; q < KP; ++q) {
-      xv[q] = ld_pack<T, VEC, true>(x + base + q * 32 * VEC);
-      gv[q] = ld_pack<T, VEC, true>(g + base + q * 32 * VEC);
-      if constexpr (EXTRAP) zv[q] = ld_pack<T, VEC, true>(zp + base + q * 32 * VEC);
+      xv[q] = nx[q];
+      gv[q] = ng[q];
+      if constexpr (EXTRAP) zv[q] = nz[q];
     }
+    if (gi + nwarps < ngroups) load_group(gi + nwarps);
     dd ss;
     ss.hi = ss.lo = 0.0;
 #pragma unroll

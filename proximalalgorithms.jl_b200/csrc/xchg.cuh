@@ -10,8 +10,7 @@
 // Wire format ("LL" style, as NCCL's low-latency protocol): every double travels as two 8-byte words {32 data bits,
 // 32-bit sequence number}.  An aligned 8-byte store is atomic on NVLink and on PCIe, so a consumer that sees the expected
 // sequence number in a word also sees its data bits -- no fences, no separate flags, and no reliance on the ORDER in
-// which posted writes become visible (a flag-after-data protocol over PCIe was observed to hand stale rows to the host
-// occasionally).
+// which posted writes become visible to a peer or to the host.
 //
 // Double buffering by the parity of the sequence number is sufficient: a rank can only complete exchange k+1 after every
 // peer has pushed k+1, which a peer does in its kernel k+1, i.e. after its kernel k (same stream) finished reading parity k.
@@ -56,22 +55,29 @@ __device__ __forceinline__ void xchg_push_wait(const XchgParams& xp, const doubl
   const int nwords = xp.world * PB_XCHG_WORDS_PER_ROW;
   if (t >= nwords) return;
   const int r = t / PB_XCHG_WORDS_PER_ROW, w = t % PB_XCHG_WORDS_PER_ROW;
-  // 1. push word w of my row into slot [par][rank] of rank r's buffer (NVLink peer store; self included)
   const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(local_block + (w >> 1)));
   const unsigned int half = (w & 1) ? (unsigned int)(bits >> 32) : (unsigned int)(bits & 0xffffffffull);
-  st_word(xp.peer[r] + ((size_t)(par * PB_MAX_RANKS + xp.rank) * PB_XCHG_WORDS_PER_ROW + w),
-          ((unsigned long long)xp.seq << 32) | half);
-  // 2. wait for word w of rank r's row in MY buffer, 3. forward it to the host
-  const unsigned long long* mine = xp.peer[xp.rank] + ((size_t)(par * PB_MAX_RANKS + r) * PB_XCHG_WORDS_PER_ROW + w);
-  const unsigned long long t0 = globaltimer_ns();
-  unsigned long long v = ld_word(mine);
-  while ((unsigned int)(v >> 32) != xp.seq) {
-    if (globaltimer_ns() - t0 > PB_XCHG_TIMEOUT_NS) {
-      v = ((unsigned long long)PB_XCHG_ERROR_SEQ << 32);
-      break;
-    }
-    __nanosleep(32);
+  const unsigned long long word = ((unsigned long long)xp.seq << 32) | half;
+  unsigned long long v;
+  if (r == xp.rank) {
+    // my own row needs no trip through memory: forward it straight to the host
+    v = word;
+  } else {
+    // 1. push word w of my row into slot [par][rank] of rank r's buffer (NVLink peer store)
+    st_word(xp.peer[r] + ((size_t)(par * PB_MAX_RANKS + xp.rank) * PB_XCHG_WORDS_PER_ROW + w), word);
+    // 2. wait for word w of rank r's row in MY buffer (busy poll: 8 bytes from L2, a handful of threads)
+    const unsigned long long* mine = xp.peer[xp.rank] + ((size_t)(par * PB_MAX_RANKS + r) * PB_XCHG_WORDS_PER_ROW + w);
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned int spins = 0;
     v = ld_word(mine);
+    while ((unsigned int)(v >> 32) != xp.seq) {
+      if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > PB_XCHG_TIMEOUT_NS) {
+        v = ((unsigned long long)PB_XCHG_ERROR_SEQ << 32);
+        break;
+      }
+      v = ld_word(mine);
+    }
   }
+  // 3. forward to the host
   st_word(xp.host_words + t, v);
 }
