@@ -186,6 +186,53 @@ int pb_lsq_blockdiag_gradient(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, 
 /* SquaredDistance (BM:19-28): grad = x - b, AUX = ||x - b||^2. */
 int pb_sqdist(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* b, void* grad);
 
+/* ---- native driver loop ---------------------------------------------------------------------------------------------
+ * The reference's IterativeAlgorithm loop (src/ProximalAlgorithms.jl:114-123) around ForwardBackward / FastForwardBackward
+ * (forward_backward.jl:65-123, fast_forward_backward.jl:73-145) with the line search of fb_tools.jl:24-63, for the built-in
+ * terms, executed inside the library: same kernel sequence and the same scalar arithmetic in R = real(eltype(x0)) as a
+ * host-language driver, without its per-iteration interpreter cost.  Scalars are read through the device exchange when one
+ * is attached to the context (any world size), else by memcpy. */
+enum { PB_F_LSQ_DENSE = 0, PB_F_LSQ_BLOCKDIAG = 1, PB_F_SQDIST = 2, PB_F_LINEAR = 3 };
+enum { PB_ALG_FB = 0, PB_ALG_FFB = 1 };
+enum { PB_SEQ_ADAPTIVE = 0, PB_SEQ_FIXED = 1, PB_SEQ_SIMPLE = 2, PB_SEQ_CONSTANT = 3 };   /* src/accel/nesterov.jl */
+
+typedef struct pb_smooth {
+  int32_t kind;          /* PB_F_*                                                                              */
+  int32_t pad;
+  int64_t m, n, lda;     /* dense: A is m x n column-major                                                      */
+  int64_t nblk, mb, nb;  /* block-diagonal: nblk column-major mb x nb blocks                                     */
+  const void* A;         /* device matrix (dense / block-diagonal)                                              */
+  const void* b;         /* device: right-hand side (least squares), b (SquaredDistance) or c (LinearFunction)   */
+  void* r;               /* device scratch for the residual: m or nblk*mb entries                               */
+} pb_smooth;
+
+typedef struct pb_solve_opts {
+  int32_t algorithm;     /* PB_ALG_*                                                                            */
+  int32_t adaptive;      /* backtracking line search on/off (fast_forward_backward.jl:50-51)                    */
+  int32_t sequence;      /* PB_SEQ_* extrapolation sequence of FFB                                              */
+  int32_t pad;
+  int64_t maxit;
+  int64_t n_global;      /* length of the whole (unsharded) iterate; 0 = n                                      */
+  double tol;            /* stop when norm(res, Inf)/gamma <= tol (negative: never)                             */
+  double gamma;          /* stepsize; <= 0: estimate 1/L with fb_tools.jl:7-12 (requires adaptive)              */
+  double mf;             /* convexity modulus seeding AdaptiveNesterovSequence                                  */
+  double constant_beta;  /* value of PB_SEQ_CONSTANT                                                            */
+  double minimum_gamma, reduce_gamma, increase_gamma;
+} pb_solve_opts;
+
+typedef struct pb_solve_result {
+  int64_t iterations;    /* k of the reference's driver loop (the init state counts as 1)                       */
+  int64_t backtracks;
+  double gamma, f_x, g_z, res_inf;
+  int32_t warned_small_gamma;   /* fb_tools.jl:59-61 would have warned                                         */
+  int32_t pad;
+  void *x, *grad, *z, *z_prev;  /* which of the caller's buffers hold the final state fields (buffers are swapped) */
+} pb_solve_result;
+
+/* x holds copy(x0) on entry.  grad, z, scratch: n-vectors.  z_prev, x_next: FFB only.  grad_z: adaptive FB only. */
+int pb_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* opts, void* x,
+             void* grad, void* z, void* z_prev, void* x_next, void* grad_z, void* scratch, pb_solve_result* result);
+
 /* ---- host-buffer convenience (the "plugin call with HOST buffers"): upload x, grad, z_prev, run K2, download z, x_next
  * and the scalar block.  All host pointers; temporary device buffers are cached in the context. */
 int pb_ffb_step_host(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev,

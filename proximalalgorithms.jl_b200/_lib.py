@@ -33,6 +33,27 @@ class pb_prox(C.Structure):
     ]
 
 
+class pb_smooth(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("m", C.c_int64), ("n", C.c_int64), ("lda", C.c_int64),
+                ("nblk", C.c_int64), ("mb", C.c_int64), ("nb", C.c_int64), ("A", C.c_void_p), ("b", C.c_void_p), ("r", C.c_void_p)]
+
+
+class pb_solve_opts(C.Structure):
+    _fields_ = [("algorithm", C.c_int32), ("adaptive", C.c_int32), ("sequence", C.c_int32), ("pad", C.c_int32),
+                ("maxit", C.c_int64), ("n_global", C.c_int64), ("tol", C.c_double), ("gamma", C.c_double), ("mf", C.c_double),
+                ("constant_beta", C.c_double), ("minimum_gamma", C.c_double), ("reduce_gamma", C.c_double), ("increase_gamma", C.c_double)]
+
+
+class pb_solve_result(C.Structure):
+    _fields_ = [("iterations", C.c_int64), ("backtracks", C.c_int64), ("gamma", C.c_double), ("f_x", C.c_double), ("g_z", C.c_double),
+                ("res_inf", C.c_double), ("warned_small_gamma", C.c_int32), ("pad", C.c_int32), ("x", C.c_void_p), ("grad", C.c_void_p),
+                ("z", C.c_void_p), ("z_prev", C.c_void_p)]
+
+
+PB_F_LSQ_DENSE, PB_F_LSQ_BLOCKDIAG, PB_F_SQDIST, PB_F_LINEAR = 0, 1, 2, 3
+PB_ALG_FB, PB_ALG_FFB = 0, 1
+PB_SEQ_ADAPTIVE, PB_SEQ_FIXED, PB_SEQ_SIMPLE, PB_SEQ_CONSTANT = 0, 1, 2, 3
+
 _vp, _i, _i64, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
 _pp = C.POINTER(pb_prox)
 
@@ -78,6 +99,8 @@ SIGNATURES = {
     "pb_lsq_blockdiag_residual": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "pb_lsq_blockdiag_gradient": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp]),
     "pb_sqdist": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "pb_solve": (_i, [_vp, _i, _i64, C.POINTER(pb_smooth), _pp, C.POINTER(pb_solve_opts), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                      C.POINTER(pb_solve_result)]),
     "pb_ffb_step_host": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _d, _d, _pp, _vp, _vp, C.POINTER(C.c_double)]),
 }
 

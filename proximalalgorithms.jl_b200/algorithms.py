@@ -404,16 +404,34 @@ def default_display(k, it, state):
 
 
 class IterativeAlgorithm:
-    """src/ProximalAlgorithms.jl:58-66, :103-123: partial application of an iterator type plus the driver loop."""
+    """src/ProximalAlgorithms.jl:58-66, :103-123: partial application of an iterator type plus the driver loop.
 
-    def __init__(self, iterator_type, maxit, stop, solution, verbose, freq, display, **kwargs):
+    `driver` (our addition): "auto" runs the loop inside the library (`pb_solve`, csrc/solve.cu) when every ingredient is
+    built in -- default stop / solution, not verbose, library smooth term, single-pass prox, known extrapolation sequence,
+    local or device exchange -- and this Python loop otherwise (user callbacks, custom stop, verbose, IndBallL2, NCCL
+    exchange).  "python" / "native" force one of them.  Both issue the same kernels and the same scalar arithmetic."""
+
+    def __init__(self, iterator_type, maxit, stop, solution, verbose, freq, display, driver="auto", **kwargs):
         self.iterator_type = iterator_type
         self.maxit, self.stop, self.solution = int(maxit), stop, solution
         self.verbose, self.freq, self.display = bool(verbose), int(freq), display
+        if driver not in ("auto", "python", "native"):
+            raise ValueError("driver must be 'auto', 'python' or 'native'")
+        self.driver = driver
         self.kwargs = kwargs
+        self.last_driver = None
 
     def __call__(self, **kwargs):
         it = self.iterator_type(**{**self.kwargs, **kwargs})                                # :115
+        if self.driver != "python":
+            out = _native_solve(self, it)
+            if out is not None:
+                self.last_driver = "native"
+                return out
+            if self.driver == "native":
+                raise L.ProxB200Error("driver='native' requested but the problem needs the Python loop "
+                                      "(user callbacks, custom stop/solution, verbose, IndBallL2 or an NCCL exchange)")
+        self.last_driver = "python"
         for k, state in enumerate(it, start=1):                                             # :116
             if k >= self.maxit or self.stop(it, state):                                     # :117
                 if self.verbose:
@@ -424,12 +442,92 @@ class IterativeAlgorithm:
                 self.display(k, it, state)
 
 
+def _native_sequence(it, R):
+    """Map the iteration's extrapolation sequence to (PB_SEQ_*, constant_beta) or None if only Python can run it."""
+    import itertools
+
+    from .nesterov import FixedNesterovSequence, SimpleNesterovSequence
+
+    seq = getattr(it, "extrapolation_sequence", None)
+    if seq is None:
+        return L.PB_SEQ_ADAPTIVE, 0.0
+    if isinstance(seq, FixedNesterovSequence) and seq.R is R:
+        return L.PB_SEQ_FIXED, 0.0
+    if isinstance(seq, SimpleNesterovSequence) and seq.R is R:
+        return L.PB_SEQ_SIMPLE, 0.0
+    if isinstance(seq, itertools.repeat):
+        return L.PB_SEQ_CONSTANT, float(R(next(seq)))
+    return None
+
+
+def _native_solve(alg, it):
+    """Run the whole solve in `pb_solve` if possible; returns (solution, iterations) or None."""
+    from .host import DeviceExchangeComm
+
+    tol = getattr(alg.stop, "_default_tol", None)
+    if tol is None or alg.solution is not default_solution or alg.verbose:
+        return None
+    f, g, R = it.f, it.g, it.R
+    if not hasattr(f, "native_descriptor") or not getattr(g, "fused", False):
+        return None
+    if g.kind not in (L.PB_PROX_ZERO, L.PB_PROX_L1, L.PB_PROX_BOX, L.PB_PROX_L21):
+        return None
+    comm = it.comm
+    if comm is not None and not isinstance(comm, (LocalComm, DeviceExchangeComm)):
+        return None
+    fdesc = f.native_descriptor()
+    if fdesc is None:
+        return None
+    fast = isinstance(it, FastForwardBackwardIteration)
+    seq = _native_sequence(it, R) if fast else (L.PB_SEQ_ADAPTIVE, 0.0)
+    if seq is None or (it.gamma is None and not it.adaptive):
+        return None
+    t = torch()
+    e = _Engine(it, it.x0)
+    if isinstance(comm, DeviceExchangeComm) and comm.ctx is not e.ctx:
+        return None
+    x = _to_device_copy(it.x0, e.ctx)
+    n = x.numel()
+    grad = f.gradient_buffer() if hasattr(f, "gradient_buffer") else t.empty_like(x)
+    check_vec(grad, n, x.dtype)
+    z, scratch = t.empty_like(x), t.empty_like(x)
+    z_prev = t.empty_like(x) if fast else None
+    x_next = t.empty_like(x) if fast and not it.adaptive else None
+    grad_z = t.empty_like(x) if (not fast and it.adaptive) else None
+    bufs = {b.data_ptr(): b for b in (x, grad, z, scratch, z_prev, x_next, grad_z) if b is not None}
+    n_glob = it.n_global if it.n_global is not None else n * e.comm.size
+    opts = L.pb_solve_opts(L.PB_ALG_FFB if fast else L.PB_ALG_FB, 1 if it.adaptive else 0, seq[0], 0, alg.maxit, int(n_glob), float(tol),
+                           0.0 if it.gamma is None else float(R(it.gamma)), float(getattr(it, "mf", 0.0)), seq[1],
+                           float(it.minimum_gamma), float(it.reduce_gamma), float(it.increase_gamma))
+    gdesc = g.descriptor(R)
+    res = L.pb_solve_result()
+    L.check(e.lib.pb_solve(e.ctx.h, pb_dtype(R), n, C.byref(fdesc), C.byref(gdesc), C.byref(opts), ptr(x), ptr(grad), ptr(z), ptr(z_prev),
+                           ptr(x_next), ptr(grad_z), ptr(scratch), C.byref(res)))
+    if res.warned_small_gamma:
+        warnings.warn(f"stepsize `gamma` became too small ({R(res.gamma)})")
+    st = FastForwardBackwardState() if fast else ForwardBackwardState()
+    st._engine, st._R = e, R
+    st.x, st.grad_f_x, st.z = bufs[res.x], bufs[res.grad], bufs[res.z]
+    if fast:
+        st.z_prev = bufs[res.z_prev]
+    st.gamma, st.f_x, st.g_z = R(res.gamma), R(res.f_x), R(res.g_z)
+
+    class _Sc:
+        res_inf = res.res_inf
+
+    st._sc = _Sc
+    it.backtracks = int(res.backtracks)
+    alg.last_iteration, alg.last_state = it, st
+    return _like_input(it.x0, st.z), int(res.iterations)
+
+
 def ForwardBackward(maxit=10_000, tol=1e-8, stop=None, solution=default_solution, verbose=False, freq=100,
                     display=default_display, **kwargs):
     """forward_backward.jl:161-179."""
     if stop is None:
         def stop(it, state, _tol=tol):
             return default_stopping_criterion(_tol, it, state)
+        stop._default_tol = tol
     return IterativeAlgorithm(ForwardBackwardIteration, maxit, stop, solution, verbose, freq, display, **kwargs)
 
 
@@ -439,6 +537,7 @@ def FastForwardBackward(maxit=10_000, tol=1e-8, stop=None, solution=default_solu
     if stop is None:
         def stop(it, state, _tol=tol):
             return default_stopping_criterion(_tol, it, state)
+        stop._default_tol = tol
     return IterativeAlgorithm(FastForwardBackwardIteration, maxit, stop, solution, verbose, freq, display, **kwargs)
 
 

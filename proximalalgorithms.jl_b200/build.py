@@ -19,11 +19,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 INCLUDE = os.path.join(ROOT, "include")
 LIBNAME = "libproxb200.so"
-SOURCES = ["ctx.cu", "step_kernels.cu", "step_tma.cu", "lsq_kernels.cu", "xchg.cu"]
+SOURCES = ["ctx.cu", "step_kernels.cu", "step_tma.cu", "lsq_kernels.cu", "xchg.cu", "solve.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-Xptxas", "-v",
     "-I", INCLUDE, "-I", CSRC,
 ]

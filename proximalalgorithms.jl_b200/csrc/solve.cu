@@ -1,0 +1,355 @@
+// solve.cu -- native driver loop: the reference's IterativeAlgorithm loop (src/ProximalAlgorithms.jl:114-123) around the
+// ForwardBackward / FastForwardBackward iterations (forward_backward.jl:65-123, fast_forward_backward.jl:73-145) and the
+// line search (fb_tools.jl:24-63), for the built-in smooth / proximable terms, entirely inside the library.
+//
+// Why it exists: the iteration is a handful of kernel launches plus ~40 scalar flops; driven from an interpreted host the
+// per-iteration host cost (tens of microseconds) is the bottleneck on small problems and at 8 GPUs.  The reference's
+// driver is compiled Julia; this is its native equivalent.  It issues the SAME kernel sequence and the SAME scalar
+// arithmetic in R = real(eltype(x0)) as the Python host (algorithms.py), so both produce identical iterates and
+// iteration counts (tests/test_gpu_solvers.py::test_native_driver_equals_python_host).
+//
+// Host-side scalar code only; every vector operation is one of the library's kernels.
+#include <math.h>
+#include <string.h>
+
+#include <limits>
+
+#include "common.cuh"
+
+namespace {
+
+struct Comb {          // rank-combined view of one exchange (mirror of host.py: Scalars)
+  double gsum, res_sq, gdr, aux, res_inf;
+  double local_aux;    // this rank's own AUX pair (dense least squares: r is replicated, not summed)
+};
+
+inline void two_sum(double a, double b, double& s, double& e) {
+  s = a + b;
+  const double bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+inline void dd_add(double& hi, double& lo, double bh, double bl) {
+  double s, e;
+  two_sum(hi, bh, s, e);
+  e += lo + bl;
+  const double h = s + e;
+  lo = e - (h - s);
+  hi = h;
+}
+inline double fold(const double* rows, int world, int slot) {
+  double hi = 0.0, lo = 0.0;
+  for (int p = 0; p < world; ++p) dd_add(hi, lo, rows[p * PB_NSCALARS + slot], rows[p * PB_NSCALARS + slot + 1]);
+  return hi + lo;
+}
+inline double fold_max(const double* rows, int world, int slot) {
+  double m = 0.0;
+  for (int p = 0; p < world; ++p) {
+    const double v = rows[p * PB_NSCALARS + slot];
+    if (v != v) return v;
+    if (v > m) m = v;
+  }
+  return m;
+}
+
+// The one host synchronisation of an iteration: device exchange when attached (any world size), else memcpy read-back.
+int read_comb(pb_ctx* ctx, Comb* c) {
+  double rows[PB_MAX_RANKS * PB_NSCALARS];
+  int world = 1, rank = 0;
+  if (ctx->xchg_world > 0 && ctx->xchg_connected) {
+    world = ctx->xchg_world;
+    rank = ctx->xchg_rank;
+    int rc = pb_exchange_wait(ctx, rows, 30.0);
+    if (rc != PB_OK) return rc;
+  } else {
+    int rc = pb_read_scalars(ctx, rows);
+    if (rc != PB_OK) return rc;
+  }
+  c->gsum = fold(rows, world, PB_S_GSUM);
+  c->res_sq = fold(rows, world, PB_S_RESSQ);
+  c->gdr = fold(rows, world, PB_S_GDR);
+  c->aux = fold(rows, world, PB_S_AUX);
+  c->res_inf = fold_max(rows, world, PB_S_RESINF);
+  c->local_aux = rows[rank * PB_NSCALARS + PB_S_AUX] + rows[rank * PB_NSCALARS + PB_S_AUX + 1];
+  return PB_OK;
+}
+
+// square root IN R (numpy's sqrt of an R scalar): sqrtf for float, sqrt for double
+inline float rs(float v) { return sqrtf(v); }
+inline double rs(double v) { return sqrt(v); }
+
+template <typename R>
+struct Nesterov {       // src/accel/nesterov.jl; same roundings as nesterov.py
+  int kind;
+  R m, stepsize, theta;   // adaptive
+  R t;                    // fixed
+  long k;                 // simple
+  R constant;
+  void init(int kind_, R mf, R constant_beta) {
+    kind = kind_;
+    m = mf;
+    stepsize = R(-1);
+    theta = R(-1);
+    t = R(1);
+    k = 1;
+    constant = constant_beta;
+  }
+  R next(R gamma) {
+    switch (kind) {
+      case PB_SEQ_FIXED: {             // nesterov.jl:14-17
+        const R t_next = (R(1) + rs(R(1) + R(4) * (t * t))) / R(2);
+        const R beta = (t - R(1)) / t_next;
+        t = t_next;
+        return beta;
+      }
+      case PB_SEQ_SIMPLE: {            // nesterov.jl:36
+        const R beta = R(k - 1) / R(k + 2);
+        ++k;
+        return beta;
+      }
+      case PB_SEQ_CONSTANT:            // nesterov.jl:51-54
+        return constant;
+      default: {                       // AdaptiveNesterovSequence, nesterov.jl:89-103
+        if (stepsize < 0) {
+          stepsize = gamma;
+          theta = m > 0 ? rs(m * gamma) : R(1);
+        }
+        const R th2 = theta * theta;
+        const R b = th2 / stepsize - m;
+        const R delta = b * b + (R(4) * th2) / (stepsize * gamma);
+        const R theta_n = (gamma * (rs(delta) - b)) / R(2);
+        const R beta = ((gamma * theta) * (R(1) - theta)) / (stepsize * theta_n + gamma * th2);
+        stepsize = gamma;
+        theta = theta_n;
+        return beta;
+      }
+    }
+  }
+};
+
+template <typename R>
+struct Solver {
+  pb_ctx* ctx;
+  int dtype;
+  int64_t n;
+  const pb_smooth* f;
+  const pb_prox* g;
+  const pb_solve_opts* o;
+  void *x, *grad, *z, *z_prev, *x_next, *grad_z, *scratch;
+  // state scalars
+  R gamma, f_x, g_z;
+  Comb sc;
+  int64_t backtracks;
+  int warned;
+
+  static R sq_half(double sum_sq) {        // norm(v)^2/2 with sqrt-then-square rounding (benchmark/benchmarks.jl:16)
+    const R nr = (R)sqrt(sum_sq);
+    return (nr * nr) / R(2);
+  }
+  R f_value(const Comb& c) const {
+    switch (f->kind) {
+      case PB_F_LSQ_DENSE: return sq_half(c.local_aux);
+      case PB_F_LINEAR: return (R)c.aux;
+      default: return sq_half(c.aux);
+    }
+  }
+  R g_value(const Comb& c) const {
+    if (g->kind == PB_PROX_L1 || g->kind == PB_PROX_L21) return (R)g->p0 * (R)c.gsum;
+    return R(0);
+  }
+  static R f_model(R fx, double gdr, double res_sq, R Lc) {     // fb_tools.jl:3-5
+    const R nr = (R)sqrt(res_sq);
+    return (fx - (R)gdr) + (Lc / R(2)) * (nr * nr);
+  }
+
+  int residual(const void* v) {     // f's residual pass at v; the value is Deferred in the AUX slot
+    switch (f->kind) {
+      case PB_F_LSQ_DENSE: return pb_lsq_dense_residual(ctx, dtype, f->m, f->n, f->A, f->lda, v, f->b, f->r);
+      case PB_F_LSQ_BLOCKDIAG: return pb_lsq_blockdiag_residual(ctx, dtype, f->nblk, f->mb, f->nb, f->A, v, f->b, f->r);
+      default: return PB_EUNSUPPORTED;
+    }
+  }
+  int eval_f(const void* v, void* grad_out) {     // value_and_gradient(f, v) -> grad_out, value Deferred
+    int rc;
+    switch (f->kind) {
+      case PB_F_LSQ_DENSE:
+        if ((rc = residual(v))) return rc;
+        return pb_lsq_dense_gradient(ctx, dtype, f->m, f->n, f->A, f->lda, f->r, grad_out);
+      case PB_F_LSQ_BLOCKDIAG:
+        if ((rc = residual(v))) return rc;
+        return pb_lsq_blockdiag_gradient(ctx, dtype, f->nblk, f->mb, f->nb, f->A, f->r, grad_out);
+      case PB_F_SQDIST:
+        return pb_sqdist(ctx, dtype, n, v, f->b, grad_out);
+      case PB_F_LINEAR:
+        if (grad_out != f->b && (rc = pb_copy(ctx, grad_out, f->b, (size_t)n * (dtype == PB_F32 ? 4 : 8)))) return rc;
+        return pb_dot(ctx, dtype, n, f->b, v);
+      default:
+        pb_set_error("pb_solve: unknown smooth term %d", f->kind);
+        return PB_EINVAL;
+    }
+  }
+  int eval_f_value(const void* v) {      // f(v) only (the FFB line search discards the gradient, fast_forward_backward.jl:112-128)
+    if (f->kind == PB_F_LSQ_DENSE || f->kind == PB_F_LSQ_BLOCKDIAG) return residual(v);
+    return eval_f(v, scratch);
+  }
+  int step(const void* xin, const void* gr, void* zout, bool extrap, R beta) {
+    if (extrap) return pb_ffb_step(ctx, dtype, n, xin, gr, z_prev, (double)gamma, (double)beta, g, nullptr, zout, nullptr, x_next);
+    return pb_fb_step(ctx, dtype, n, xin, gr, (double)gamma, g, nullptr, zout, nullptr);
+  }
+  bool stop() const {                    // norm(res, Inf)/gamma <= tol
+    const R rn = (R)sc.res_inf;
+    return (double)(rn / gamma) <= o->tol;
+  }
+
+  // fb_tools.jl:24-63 (A = nothing, Az aliased to z).  want_grad: FB keeps grad f(z) in grad_z.
+  int backtrack(bool want_grad, R* f_z_out) {
+    const R eps = std::numeric_limits<R>::epsilon();
+    int rc;
+    R f_upp = f_model(f_x, sc.gdr, sc.res_sq, R(1) / gamma);
+    if ((rc = want_grad ? eval_f(z, grad_z) : eval_f_value(z))) return rc;
+    Comb c;
+    if ((rc = read_comb(ctx, &c))) return rc;
+    R f_z = f_value(c);
+    R tol = R(10) * eps * (R(1) + (R)fabs((double)f_z));
+    while (f_z > f_upp + tol && gamma >= (R)o->minimum_gamma) {
+      gamma = gamma * (R)o->reduce_gamma;
+      if ((rc = step(x, grad, z, false, R(0)))) return rc;
+      if ((rc = read_comb(ctx, &sc))) return rc;
+      g_z = g_value(sc);
+      f_upp = f_model(f_x, sc.gdr, sc.res_sq, R(1) / gamma);
+      if ((rc = want_grad ? eval_f(z, grad_z) : eval_f_value(z))) return rc;
+      if ((rc = read_comb(ctx, &c))) return rc;
+      f_z = f_value(c);
+      tol = R(10) * eps * (R(1) + (R)fabs((double)f_z));
+      ++backtracks;
+    }
+    if (gamma < (R)o->minimum_gamma) warned = 1;     // fb_tools.jl:59-61 (the host prints the warning)
+    *f_z_out = f_z;
+    return PB_OK;
+  }
+
+  int run(pb_solve_result* out) {
+    int rc;
+    const bool fast = o->algorithm == PB_ALG_FFB;
+    const bool adaptive = o->adaptive != 0;
+    backtracks = 0;
+    warned = 0;
+    // ---- init: forward_backward.jl:65-84 / fast_forward_backward.jl:73-97 ----
+    if ((rc = eval_f(x, grad))) return rc;
+    bool fx_pending = true;
+    if (o->gamma <= 0) {                 // fb_tools.jl:7-12 with A = I
+      if ((rc = read_comb(ctx, &sc))) return rc;
+      f_x = f_value(sc);
+      fx_pending = false;
+      if ((rc = pb_add_scalar(ctx, dtype, n, x, 1.0, scratch))) return rc;
+      if ((rc = eval_f(scratch, z))) return rc;                      // z is free at this point: holds grad f(x + 1)
+      if ((rc = pb_sub(ctx, dtype, n, z, grad, z))) return rc;
+      Comb c2;
+      if ((rc = read_comb(ctx, &c2))) return rc;
+      const int64_t n_glob = o->n_global > 0 ? o->n_global : n;
+      const R lower = (R)sqrt(c2.aux) / (R)sqrt((double)n_glob);
+      gamma = R(1) / lower;
+    } else {
+      gamma = (R)o->gamma;
+    }
+    Nesterov<R> seq;
+    seq.init(o->sequence, (R)o->mf, (R)o->constant_beta);
+    R beta_next = R(0);
+    if (fast) {
+      if ((rc = pb_copy(ctx, z_prev, x, (size_t)n * (dtype == PB_F32 ? 4 : 8)))) return rc;     // z_prev = copy(x)
+      if (!adaptive) {
+        beta_next = seq.next(gamma);
+        rc = step(x, grad, z, true, beta_next);
+      } else {
+        rc = step(x, grad, z, false, R(0));
+      }
+    } else {
+      rc = step(x, grad, z, false, R(0));
+    }
+    if (rc) return rc;
+    if ((rc = read_comb(ctx, &sc))) return rc;
+    if (fx_pending) f_x = f_value(sc);
+    g_z = g_value(sc);
+    // ---- driver loop: src/ProximalAlgorithms.jl:114-123 ----
+    int64_t k = 1;
+    for (;; ++k) {
+      if (k >= o->maxit || stop()) break;
+      if (!fast) {                       // forward_backward.jl:86-123
+        if (adaptive) {
+          gamma = gamma * (R)o->increase_gamma;
+          R f_z;
+          if ((rc = backtrack(true, &f_z))) return rc;
+          f_x = f_z;
+          void* t = x; x = z; z = t;
+          t = grad; grad = grad_z; grad_z = t;
+          if ((rc = step(x, grad, z, false, R(0)))) return rc;
+          if ((rc = read_comb(ctx, &sc))) return rc;
+        } else {
+          void* t = x; x = z; z = t;
+          if ((rc = eval_f(x, grad))) return rc;
+          if ((rc = step(x, grad, z, false, R(0)))) return rc;
+          if ((rc = read_comb(ctx, &sc))) return rc;
+          f_x = f_value(sc);
+        }
+        g_z = g_value(sc);
+      } else {                           // fast_forward_backward.jl:106-145
+        if (adaptive) {
+          gamma = gamma * (R)o->increase_gamma;
+          R f_z;
+          if ((rc = backtrack(false, &f_z))) return rc;
+          const R beta = seq.next(gamma);
+          if ((rc = pb_extrapolate(ctx, dtype, n, z, z_prev, (double)beta, x))) return rc;
+          void* t = z_prev; z_prev = z; z = t;
+          if ((rc = eval_f(x, grad))) return rc;
+          if ((rc = step(x, grad, z, false, R(0)))) return rc;
+        } else {
+          gamma = (R)o->gamma > 0 ? (R)o->gamma : gamma;
+          void* t = x; x = x_next; x_next = t;        // :135, computed by the previous fused pass
+          t = z_prev; z_prev = z; z = t;              // :136
+          if ((rc = eval_f(x, grad))) return rc;
+          beta_next = seq.next(gamma);
+          if ((rc = step(x, grad, z, true, beta_next))) return rc;
+        }
+        if ((rc = read_comb(ctx, &sc))) return rc;
+        f_x = f_value(sc);
+        g_z = g_value(sc);
+      }
+    }
+    out->iterations = k;
+    out->gamma = (double)gamma;
+    out->f_x = (double)f_x;
+    out->g_z = (double)g_z;
+    out->res_inf = sc.res_inf;
+    out->backtracks = backtracks;
+    out->warned_small_gamma = warned;
+    out->x = x;
+    out->grad = grad;
+    out->z = z;
+    out->z_prev = z_prev;
+    return PB_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" int pb_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o,
+                        void* x, void* grad, void* z, void* z_prev, void* x_next, void* grad_z, void* scratch,
+                        pb_solve_result* out) {
+  PB_REQUIRE(ctx != nullptr && f != nullptr && g != nullptr && o != nullptr && out != nullptr, "null argument");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  PB_REQUIRE(n >= 0 && o->maxit >= 1, "need n >= 0 and maxit >= 1");
+  PB_REQUIRE(x && grad && z && scratch, "null state vector");
+  PB_REQUIRE(o->algorithm == PB_ALG_FB || o->algorithm == PB_ALG_FFB, "unknown algorithm");
+  PB_REQUIRE(o->algorithm != PB_ALG_FFB || (z_prev && (o->adaptive || x_next)), "FFB needs z_prev (and x_next when the stepsize is fixed)");
+  PB_REQUIRE(o->algorithm != PB_ALG_FB || !o->adaptive || grad_z, "adaptive FB needs grad_z");
+  PB_REQUIRE(o->gamma > 0 || o->adaptive, "a fixed stepsize needs gamma > 0");
+  PB_REQUIRE(g->kind == PB_PROX_ZERO || g->kind == PB_PROX_L1 || g->kind == PB_PROX_BOX || g->kind == PB_PROX_L21,
+             "pb_solve supports the single-pass prox kinds (Zero, NormL1, IndBox, NormL21)");
+  PB_REQUIRE(f->kind != PB_F_LSQ_DENSE || ctx->xchg_world <= 1, "dense least squares is single-GPU in pb_solve (column shards need a vector all-gather)");
+  memset(out, 0, sizeof(*out));
+  if (dtype == PB_F32) {
+    Solver<float> s{ctx, dtype, n, f, g, o, x, grad, z, z_prev, x_next, grad_z, scratch};
+    return s.run(out);
+  }
+  Solver<double> s{ctx, dtype, n, f, g, o, x, grad, z, z_prev, x_next, grad_z, scratch};
+  return s.run(out);
+}

@@ -128,6 +128,12 @@ class LeastSquares:
         self.calls += 1
         return self._residual(x)
 
+    def native_descriptor(self):
+        """pb_smooth for the native driver (single GPU only: column shards need a vector all-gather per evaluation)."""
+        if self.comm.size != 1:
+            return None
+        return L.pb_smooth(L.PB_F_LSQ_DENSE, 0, self.m, self.n, self.m, 0, 0, 0, self.A_cm.data_ptr(), self.b.data_ptr(), self.r.data_ptr())
+
     def value_and_gradient(self, x):
         """Reference-shaped allocating form."""
         grad = torch().empty_like(x)
@@ -165,6 +171,9 @@ class BlockDiagLeastSquares:
         cm = t.as_tensor(np.ascontiguousarray(np.transpose(blocks, (0, 2, 1)))).to(ctx.device)
         return cls(cm, t.as_tensor(np.ascontiguousarray(b)).to(ctx.device), comm=comm)
 
+    def native_descriptor(self):
+        return L.pb_smooth(L.PB_F_LSQ_BLOCKDIAG, 0, 0, 0, 0, self.nblk, self.mb, self.nb, self.A.data_ptr(), self.b.data_ptr(), self.r.data_ptr())
+
     def _residual(self, ctx, x):
         check_vec(x, self.n, self.A.dtype)
         L.check(ctx.lib.pb_lsq_blockdiag_residual(ctx.h, pb_dtype(self.R), self.nblk, self.mb, self.nb, ptr(self.A), ptr(x), ptr(self.b), ptr(self.r)))
@@ -194,6 +203,9 @@ class SquaredDistance:
         self.b = _as_device(b, self.ctx.device).contiguous()
         self.R = real_type(self.b.dtype)
 
+    def native_descriptor(self):
+        return L.pb_smooth(L.PB_F_SQDIST, 0, 0, 0, 0, 0, 0, 0, None, self.b.data_ptr(), None)
+
     def value_and_gradient_into(self, ctx, x, grad):
         check_vec(x, self.b.numel(), self.b.dtype)
         L.check(ctx.lib.pb_sqdist(ctx.h, pb_dtype(self.R), x.numel(), ptr(x), ptr(self.b), ptr(grad)))
@@ -207,8 +219,8 @@ class SquaredDistance:
 
 class LinearFunction:
     """f(x) = <c, x>: constant gradient c.  This is the "gradient supplied as a buffer" smooth term of the fused-step-only
-    workloads (BASELINE.json configs[2]): value_and_gradient_into leaves `grad` aliasing... no copy
-    is made when the iteration's gradient buffer IS `c` (see algorithms._eval_f)."""
+    workloads (BASELINE.json configs[2]): no copy is made when the iteration's gradient buffer IS
+    `c` (`gradient_buffer`)."""
 
     def __init__(self, c):
         self.c = c
@@ -217,6 +229,9 @@ class LinearFunction:
 
     def gradient_buffer(self):
         return self.c
+
+    def native_descriptor(self):
+        return L.pb_smooth(L.PB_F_LINEAR, 0, 0, 0, 0, 0, 0, 0, None, self.c.data_ptr(), None)
 
     def value_and_gradient_into(self, ctx, x, grad):
         if grad.data_ptr() != self.c.data_ptr():

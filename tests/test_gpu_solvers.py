@@ -266,3 +266,58 @@ def test_config2_blockdiag_lasso_fista(T):
         assert it == it_o and np.max(np.abs(z - z_o)) <= 1e-9
     else:
         assert abs(it - it_o) <= max(2, it_o // 100) and np.max(np.abs(z - z_o)) <= 1e-4
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_native_driver_equals_python_host(T):
+    """The in-library driver loop (pb_solve, csrc/solve.cu) and the Python loop issue the same kernels and the same scalar
+    arithmetic in R: identical iteration counts and bit-identical solutions, for every algorithm variant."""
+    d = load_golden("lasso_small")
+    A, b, lam = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T), T(d["lam"])
+    Lf = T(np.linalg.norm(d["A"], 2) ** 2)
+    tol = T(1e-6 if T == np.float64 else 1e-4)
+    x0 = np.zeros(A.shape[1], T)
+    cases = [
+        (pa.FastForwardBackward, {}),
+        (pa.FastForwardBackward, dict(increase_gamma=T(1.01))),
+        (pa.FastForwardBackward, dict(Lf=Lf)),
+        (pa.FastForwardBackward, dict(Lf=Lf, mf=T(0.01))),
+        (pa.FastForwardBackward, dict(Lf=Lf, extrapolation_sequence=pa.FixedNesterovSequence(T))),
+        (pa.FastForwardBackward, dict(Lf=Lf, extrapolation_sequence=pa.SimpleNesterovSequence(T))),
+        (pa.FastForwardBackward, dict(Lf=Lf, extrapolation_sequence=pa.ConstantNesterovSequence(T(0.05), T(1) / Lf))),
+        (pa.ForwardBackward, {}),
+        (pa.ForwardBackward, dict(increase_gamma=T(1.01))),
+        (pa.ForwardBackward, dict(Lf=Lf)),
+    ]
+    for mk, kw in cases:
+        for g in (pa.NormL1(lam), pa.IndBox(T(-0.05), T(0.05)), pa.NormL21(lam, 4), pa.Zero()):
+            f = pa.LeastSquares(A, b)
+            kw_p = dict(kw)
+            if "extrapolation_sequence" in kw_p and isinstance(kw_p["extrapolation_sequence"], type(iter(()))):
+                pass
+            sol_p, sol_n = mk(tol=tol, maxit=600, driver="python"), mk(tol=tol, maxit=600, driver="native")
+            zp, itp = sol_p(x0=x0, f=f, g=g, **kw)
+            if "extrapolation_sequence" in kw and not hasattr(kw["extrapolation_sequence"], "R"):
+                kw = dict(kw, extrapolation_sequence=pa.ConstantNesterovSequence(T(0.05), T(1) / Lf))   # itertools.repeat is stateless
+            zn, itn = sol_n(x0=x0, f=f, g=g, **kw)
+            assert sol_p.last_driver == "python" and sol_n.last_driver == "native"
+            assert itn == itp, (mk.__name__, kw.keys(), type(g).__name__, itn, itp)
+            assert np.array_equal(zn, zp, equal_nan=True)
+            sn, sp = sol_n.last_state, sol_p.last_state
+            assert sn.gamma == sp.gamma and sn.f_x == sp.f_x and sn.g_z == sp.g_z and float(sn.res_norm_inf) == float(sp.res_norm_inf)
+            assert torch.equal(sn.x, sp.x) and torch.equal(sn.grad_f_x, sp.grad_f_x)
+    # other built-in smooth terms
+    rng = np.random.default_rng(0)
+    bvec = rng.standard_normal(5000).astype(T)
+    for f in (pa.SquaredDistance(torch.as_tensor(bvec).cuda()),
+              pa.BlockDiagLeastSquares.from_numpy((rng.standard_normal((5, 8, 1000)) / 3).astype(T), rng.standard_normal(40).astype(T))):
+        for mk, kw in ((pa.FastForwardBackward, {}), (pa.ForwardBackward, {}), (pa.FastForwardBackward, dict(gamma=T(0.05)))):
+            zp, itp = mk(tol=tol, maxit=300, driver="python")(x0=np.zeros(5000, T), f=f, g=pa.NormL1(T(0.3)), **kw)
+            zn, itn = mk(tol=tol, maxit=300, driver="native")(x0=np.zeros(5000, T), f=f, g=pa.NormL1(T(0.3)), **kw)
+            assert itn == itp and np.array_equal(zn, zp)
+    # what the native driver cannot run falls back (auto) or refuses (native)
+    auto = pa.FastForwardBackward(tol=tol, maxit=50)
+    auto(x0=x0, f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)), Lf=Lf)
+    assert auto.last_driver == "python"
+    with pytest.raises(pa.ProxB200Error):
+        pa.FastForwardBackward(tol=tol, driver="native")(x0=x0, f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)), Lf=Lf)
