@@ -292,13 +292,8 @@ def test_native_driver_equals_python_host(T):
     for mk, kw in cases:
         for g in (pa.NormL1(lam), pa.IndBox(T(-0.05), T(0.05)), pa.NormL21(lam, 4), pa.Zero()):
             f = pa.LeastSquares(A, b)
-            kw_p = dict(kw)
-            if "extrapolation_sequence" in kw_p and isinstance(kw_p["extrapolation_sequence"], type(iter(()))):
-                pass
             sol_p, sol_n = mk(tol=tol, maxit=600, driver="python"), mk(tol=tol, maxit=600, driver="native")
             zp, itp = sol_p(x0=x0, f=f, g=g, **kw)
-            if "extrapolation_sequence" in kw and not hasattr(kw["extrapolation_sequence"], "R"):
-                kw = dict(kw, extrapolation_sequence=pa.ConstantNesterovSequence(T(0.05), T(1) / Lf))   # itertools.repeat is stateless
             zn, itn = sol_n(x0=x0, f=f, g=g, **kw)
             assert sol_p.last_driver == "python" and sol_n.last_driver == "native"
             assert itn == itp, (mk.__name__, kw.keys(), type(g).__name__, itn, itp)
