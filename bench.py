@@ -315,7 +315,7 @@ def run_b200(args):
             "h2d_bytes_per_step": int(2 * 4 * n * world / K), "d2h_bytes_per_step": int((4 * n * world + 128 * K * world) / K),
             "what": f"FastForwardBackward(maxit={K}, tol<0)(x0=host, f=SquaredDistance(host b), g=NormL1(1), gamma=1): pinned host x0,b "
                     f"-> device, {K} iterations (sqdist gradient kernel + fused step + scalar read-back each), solution -> host; wall clock, max over ranks",
-            "seconds": dt,
+            "seconds": dt, "driver": solver.last_driver, "phases": getattr(solver, "last_timing", None),
         }
         # the literal single-call form: one fused step through the C ABI with HOST buffers (N=1 only; PCIe bound)
         if world == 1:

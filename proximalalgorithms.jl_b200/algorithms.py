@@ -66,7 +66,7 @@ class _Engine:
         t = torch()
         dev = x0.device if isinstance(x0, t.Tensor) and x0.is_cuda else None
         self.ctx = Context.get(dev)
-        self.comm = it.comm or LocalComm()
+        self.comm = it.comm if it.comm is not None else self.ctx.default_comm()
         self.lib = self.ctx.lib
 
     # ---- smooth term ---------------------------------------------------------------------------------------------
@@ -482,10 +482,15 @@ def _native_solve(alg, it):
     seq = _native_sequence(it, R) if fast else (L.PB_SEQ_ADAPTIVE, 0.0)
     if seq is None or (it.gamma is None and not it.adaptive):
         return None
+    import time
+
     t = torch()
     e = _Engine(it, it.x0)
-    if isinstance(comm, DeviceExchangeComm) and comm.ctx is not e.ctx:
+    if isinstance(e.comm, DeviceExchangeComm) and e.comm.ctx is not e.ctx:
         return None
+    if isinstance(e.comm, LocalComm) and getattr(e.ctx, "_xchg_comm", None) is not None:
+        return None           # pb_solve reads through the attached exchange; an explicit memcpy read-back needs the Python loop
+    t0 = time.perf_counter()
     x = _to_device_copy(it.x0, e.ctx)
     n = x.numel()
     grad = f.gradient_buffer() if hasattr(f, "gradient_buffer") else t.empty_like(x)
@@ -501,8 +506,10 @@ def _native_solve(alg, it):
                            float(it.minimum_gamma), float(it.reduce_gamma), float(it.increase_gamma))
     gdesc = g.descriptor(R)
     res = L.pb_solve_result()
+    t1 = time.perf_counter()
     L.check(e.lib.pb_solve(e.ctx.h, pb_dtype(R), n, C.byref(fdesc), C.byref(gdesc), C.byref(opts), ptr(x), ptr(grad), ptr(z), ptr(z_prev),
                            ptr(x_next), ptr(grad_z), ptr(scratch), C.byref(res)))
+    t2 = time.perf_counter()
     if res.warned_small_gamma:
         warnings.warn(f"stepsize `gamma` became too small ({R(res.gamma)})")
     st = FastForwardBackwardState() if fast else ForwardBackwardState()
@@ -518,7 +525,10 @@ def _native_solve(alg, it):
     st._sc = _Sc
     it.backtracks = int(res.backtracks)
     alg.last_iteration, alg.last_state = it, st
-    return _like_input(it.x0, st.z), int(res.iterations)
+    sol = _like_input(it.x0, st.z)
+    # host-side wall clock of the phases (pb_solve returns after its last scalar read, i.e. with the stream drained)
+    alg.last_timing = {"upload_and_alloc_s": t1 - t0, "pb_solve_s": t2 - t1, "download_s": time.perf_counter() - t2}
+    return sol, int(res.iterations)
 
 
 def ForwardBackward(maxit=10_000, tol=1e-8, stop=None, solution=default_solution, verbose=False, freq=100,

@@ -145,19 +145,23 @@ class DeviceExchangeComm:
     `exchange` only polls a pinned flag.  No collective launch, no cudaMemcpy, no stream synchronisation per iteration.
     torch.distributed is used once, to all-gather the 64-byte IPC handles.  World size 1 = zero-copy read-back."""
 
-    def __init__(self, ctx, group=None, fused=True):
+    def __init__(self, ctx, group=None, fused=True, standalone=False):
         t = torch()
         self.group = group
         self.dist = None
         self.rank, self.size = 0, 1
-        if t.distributed.is_available() and t.distributed.is_initialized():
+        self.standalone = standalone
+        if not standalone and t.distributed.is_available() and t.distributed.is_initialized():
             self.dist = t.distributed
             self.rank = self.dist.get_rank(group)
             self.size = self.dist.get_world_size(group)
         if self.size > L.PB_MAX_WORLD:
             raise ValueError(f"DeviceExchangeComm supports at most {L.PB_MAX_WORLD} ranks")
-        if getattr(ctx, "_xchg_comm", None) is not None:
-            raise L.ProxB200Error("this context already owns a device exchange")
+        prev = getattr(ctx, "_xchg_comm", None)
+        if prev is not None:
+            if not prev.standalone:
+                raise L.ProxB200Error("this context already owns a device exchange")
+            prev.close()          # the implicit single-GPU exchange makes way for an explicit one
         handle = C.create_string_buffer(L.PB_IPC_HANDLE_BYTES)
         L.check(ctx.lib.pb_xchg_init(ctx.h, self.rank, self.size, handle))
         if self.size > 1:
@@ -244,6 +248,16 @@ class Context:
         self.scal = t.zeros(L.PB_NSCALARS, dtype=t.float64, device=self.device)
         L.check(self.lib.pb_ctx_set_scalars_dev(self.h, C.c_void_p(self.scal.data_ptr())))
         self._host = (C.c_double * L.PB_NSCALARS)()
+
+    def default_comm(self):
+        """Exchange used when an iteration is given no `comm`: the world-of-one device exchange (zero-copy read-back of the
+        scalar block through mapped pinned memory, pushed by the step kernel itself) -- created once per context."""
+        cur = getattr(self, "_xchg_comm", None)
+        if cur is not None and cur.size == 1:
+            return cur
+        if cur is not None:
+            return LocalComm()    # a multi-rank exchange is attached: an un-sharded solve reads back by memcpy
+        return DeviceExchangeComm(self, standalone=True)
 
     def read_scalars(self) -> np.ndarray:
         L.check(self.lib.pb_read_scalars(self.h, self._host))

@@ -306,10 +306,10 @@ def test_native_driver_equals_python_host(T):
     bvec = rng.standard_normal(5000).astype(T)
     for f in (pa.SquaredDistance(torch.as_tensor(bvec).cuda()),
               pa.BlockDiagLeastSquares.from_numpy((rng.standard_normal((5, 8, 1000)) / 3).astype(T), rng.standard_normal(40).astype(T))):
-        for mk, kw in ((pa.FastForwardBackward, {}), (pa.ForwardBackward, {}), (pa.FastForwardBackward, dict(gamma=T(0.05)))):
+        for mk, kw in ((pa.FastForwardBackward, {}), (pa.ForwardBackward, {}), (pa.FastForwardBackward, dict(gamma=T(0.005)))):
             zp, itp = mk(tol=tol, maxit=300, driver="python")(x0=np.zeros(5000, T), f=f, g=pa.NormL1(T(0.3)), **kw)
             zn, itn = mk(tol=tol, maxit=300, driver="native")(x0=np.zeros(5000, T), f=f, g=pa.NormL1(T(0.3)), **kw)
-            assert itn == itp and np.array_equal(zn, zp)
+            assert itn == itp and np.array_equal(zn, zp, equal_nan=True) and np.all(np.isfinite(zn))
     # what the native driver cannot run falls back (auto) or refuses (native)
     auto = pa.FastForwardBackward(tol=tol, maxit=50)
     auto(x0=x0, f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)), Lf=Lf)
