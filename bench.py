@@ -8,8 +8,10 @@ Workload (BASELINE.json metric: "prox-grad iterations/sec and fused-step HBM GB/
 FISTA + NormL1(lambda=1), n = 10^8 Float32 in total, gamma = 0.1, beta = 0.5, x, grad, z_prev ~ synthetic, the gradient
 supplied as a resident buffer ("fused step only").  One step = one iteration of the inner loop: the fused
 grad-step + prox + extrapolation kernel (pb_ffb_step, 5 vector streams = 20 B/element) followed by the per-iteration
-scalar read-back that the driver loop's stop test needs (at N > 1: the all-gather of the scalar block).  With N GPUs the
-iterate is row-sharded over the ranks (strong scaling: n is fixed).
+scalar exchange and the host-side stop test of the driver loop.  The loop is the product's own (pb_solve, reached through
+pa.FastForwardBackward(maxit=K, tol<0)(x0=..., f=LinearFunction(c), g=NormL1(1), gamma=0.1, extrapolation_sequence=
+repeat(0.5)) on device-resident tensors); `--loop python` spells the same iteration out in this file instead.  With N GPUs
+the iterate is row-sharded over the ranks (strong scaling: n is fixed).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
 """
@@ -46,6 +48,9 @@ def parse():
     p.add_argument("--n", type=int, default=N_TOTAL)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--loop", default="native", choices=["native", "python"],
+                   help="native = the library's driver loop pb_solve through pa.FastForwardBackward (default); "
+                        "python = the same iteration spelled out in this file (pb_ffb_step + exchange per step)")
     p.add_argument("--exchange", default="device", choices=["device", "nccl", "memcpy"],
                    help="per-iteration scalar exchange: device = in-kernel NVLink push + pinned-flag poll (default); "
                         "nccl = all_gather + D2H copy; memcpy = cudaMemcpy read-back (N=1 only)")
@@ -237,23 +242,51 @@ def run_b200(args):
         s["z_prev"], s["z"] = s["z"], s["z_prev"]
         return sc
 
-    for _ in range(max(3, args.warmup)):
-        step()
     K = args.steps
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = ctx.launches()
-    barrier()
-    e0.record()
-    for k in range(K):
-        sc = step(evs[k])
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launches() - launches0
+    sampler = None
+    if args.loop == "native":
+        # The product's own driver loop (pb_solve, csrc/solve.cu) through the public solver API, on device-resident tensors:
+        # f = <c, x> makes c the "supplied gradient buffer", beta = 0.5 is a constant extrapolation sequence, tol < 0 never
+        # stops, so K iterations = K launches of K2, each followed by the scalar exchange and the host stop test.
+        import itertools
+
+        f_lin = pa.LinearFunction(grad)
+        kw = dict(x0=x, f=f_lin, g=pa.NormL1(LAMBDA), gamma=GAMMA, extrapolation_sequence=itertools.repeat(np.float32(BETA)),
+                  comm=comm, n_global=args.n)
+        warm = pa.FastForwardBackward(maxit=max(3, args.warmup), tol=-1.0, driver="native")
+        warm(**kw)
+        del warm
+        solver = pa.FastForwardBackward(maxit=K, tol=-1.0, driver="native")
+        solver.profile = True            # CUDA events inside pb_solve: around the K iterations and around every K2 launch
+        sampler = ClockSampler(local) if rank == 0 else None
+        launches0 = ctx.launches()
+        barrier()
+        zsol, its = solver(**kw)
+        barrier()
+        assert its == K
+        launches = ctx.launches() - launches0
+        tm = solver.last_timing
+        ms_total, kern_ms = tm["loop_ms"], tm["step_kernel_ms"] / max(1, tm["step_kernel_launches"])
+        last_res_inf = float(solver.last_state.res_norm_inf)
+        del zsol
+    else:
+        for _ in range(max(3, args.warmup)):
+            step()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local) if rank == 0 else None
+        launches0 = ctx.launches()
+        barrier()
+        e0.record()
+        for k in range(K):
+            sc = step(evs[k])
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = ctx.launches() - launches0
+        kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        last_res_inf = sc.res_inf
     clocks = sampler.stop() if sampler else None
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     t = torch.tensor([ms_total, kern_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,7 +387,9 @@ def run_b200(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "M3 Lasso FISTA fused-step-only: n=1e8 fp32 total, NormL1(1), gamma=0.1, beta=0.5, gradient supplied as a resident buffer; "
-                                   "step = pb_ffb_step + per-iteration scalar read-back" + (" (all-gather of the scalar block)" if world > 1 else ""),
+                                   "step = one iteration of the inner loop = pb_ffb_step (K2) + per-iteration scalar exchange + host stop test" +
+                                   (", driven by the library's loop pb_solve via pa.FastForwardBackward(maxit=K, tol<0, driver=native)" if args.loop == "native" else ", driven by a Python loop in bench.py"),
+                       "loop": args.loop,
                        "n": args.n, "n_per_gpu": n, "parallelism": f"row-shard x{world}", "exchange": args.exchange, "l2": "inputs exceed L2 (5 x %.0f MB streams per GPU)" % (4 * n / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "kernel": "k_step<float, L1, EXTRAP> (pb_ffb_step)", "kernel_ms": kern_ms_max,
@@ -367,7 +402,7 @@ def run_b200(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "last_residual_inf": sc.res_inf,
+            "last_residual_inf": last_res_inf,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

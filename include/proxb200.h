@@ -210,7 +210,7 @@ typedef struct pb_solve_opts {
   int32_t algorithm;     /* PB_ALG_*                                                                            */
   int32_t adaptive;      /* backtracking line search on/off (fast_forward_backward.jl:50-51)                    */
   int32_t sequence;      /* PB_SEQ_* extrapolation sequence of FFB                                              */
-  int32_t pad;
+  int32_t profile;       /* 1: time the loop and every fused-step launch with CUDA events (result->loop_ms, ...)  */
   int64_t maxit;
   int64_t n_global;      /* length of the whole (unsharded) iterate; 0 = n                                      */
   double tol;            /* stop when norm(res, Inf)/gamma <= tol (negative: never)                             */
@@ -227,6 +227,9 @@ typedef struct pb_solve_result {
   int32_t warned_small_gamma;   /* fb_tools.jl:59-61 would have warned                                         */
   int32_t pad;
   void *x, *grad, *z, *z_prev;  /* which of the caller's buffers hold the final state fields (buffers are swapped) */
+  double loop_ms;               /* opts->profile: CUDA-event time from the first kernel of init to the last kernel  */
+  double step_kernel_ms;        /* opts->profile: summed CUDA-event time of the timed fused-step launches            */
+  int64_t step_kernel_launches; /* opts->profile: how many launches that sum covers (at most 4096)                   */
 } pb_solve_result;
 
 /* x holds copy(x0) on entry.  grad, z, scratch: n-vectors.  z_prev, x_next: FFB only.  grad_z: adaptive FB only. */

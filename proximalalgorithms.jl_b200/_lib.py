@@ -39,7 +39,7 @@ class pb_smooth(C.Structure):
 
 
 class pb_solve_opts(C.Structure):
-    _fields_ = [("algorithm", C.c_int32), ("adaptive", C.c_int32), ("sequence", C.c_int32), ("pad", C.c_int32),
+    _fields_ = [("algorithm", C.c_int32), ("adaptive", C.c_int32), ("sequence", C.c_int32), ("profile", C.c_int32),
                 ("maxit", C.c_int64), ("n_global", C.c_int64), ("tol", C.c_double), ("gamma", C.c_double), ("mf", C.c_double),
                 ("constant_beta", C.c_double), ("minimum_gamma", C.c_double), ("reduce_gamma", C.c_double), ("increase_gamma", C.c_double)]
 
@@ -47,7 +47,8 @@ class pb_solve_opts(C.Structure):
 class pb_solve_result(C.Structure):
     _fields_ = [("iterations", C.c_int64), ("backtracks", C.c_int64), ("gamma", C.c_double), ("f_x", C.c_double), ("g_z", C.c_double),
                 ("res_inf", C.c_double), ("warned_small_gamma", C.c_int32), ("pad", C.c_int32), ("x", C.c_void_p), ("grad", C.c_void_p),
-                ("z", C.c_void_p), ("z_prev", C.c_void_p)]
+                ("z", C.c_void_p), ("z_prev", C.c_void_p), ("loop_ms", C.c_double), ("step_kernel_ms", C.c_double),
+                ("step_kernel_launches", C.c_int64)]
 
 
 PB_F_LSQ_DENSE, PB_F_LSQ_BLOCKDIAG, PB_F_SQDIST, PB_F_LINEAR = 0, 1, 2, 3

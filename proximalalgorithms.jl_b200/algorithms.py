@@ -501,7 +501,7 @@ def _native_solve(alg, it):
     grad_z = t.empty_like(x) if (not fast and it.adaptive) else None
     bufs = {b.data_ptr(): b for b in (x, grad, z, scratch, z_prev, x_next, grad_z) if b is not None}
     n_glob = it.n_global if it.n_global is not None else n * e.comm.size
-    opts = L.pb_solve_opts(L.PB_ALG_FFB if fast else L.PB_ALG_FB, 1 if it.adaptive else 0, seq[0], 0, alg.maxit, int(n_glob), float(tol),
+    opts = L.pb_solve_opts(L.PB_ALG_FFB if fast else L.PB_ALG_FB, 1 if it.adaptive else 0, seq[0], 1 if getattr(alg, "profile", False) else 0, alg.maxit, int(n_glob), float(tol),
                            0.0 if it.gamma is None else float(R(it.gamma)), float(getattr(it, "mf", 0.0)), seq[1],
                            float(it.minimum_gamma), float(it.reduce_gamma), float(it.increase_gamma))
     gdesc = g.descriptor(R)
@@ -528,6 +528,8 @@ def _native_solve(alg, it):
     sol = _like_input(it.x0, st.z)
     # host-side wall clock of the phases (pb_solve returns after its last scalar read, i.e. with the stream drained)
     alg.last_timing = {"upload_and_alloc_s": t1 - t0, "pb_solve_s": t2 - t1, "download_s": time.perf_counter() - t2}
+    if getattr(alg, "profile", False):
+        alg.last_timing.update(loop_ms=res.loop_ms, step_kernel_ms=res.step_kernel_ms, step_kernel_launches=int(res.step_kernel_launches))
     return sol, int(res.iterations)
 
 

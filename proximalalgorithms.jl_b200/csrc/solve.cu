@@ -140,6 +140,13 @@ struct Solver {
   Comb sc;
   int64_t backtracks;
   int warned;
+  bool lazy_value;                       // LinearFunction with a fixed stepsize: f(x) is never consumed inside the loop
+  // optional profiling (opts->profile): CUDA events around the whole loop and around every fused-step launch
+  static const int kMaxStepEvents = 4096;
+  cudaEvent_t ev_loop[2];
+  cudaEvent_t* ev_step;
+  int n_step_events;
+  bool profile;
 
   static R sq_half(double sum_sq) {        // norm(v)^2/2 with sqrt-then-square rounding (benchmark/benchmarks.jl:16)
     const R nr = (R)sqrt(sum_sq);
@@ -181,6 +188,7 @@ struct Solver {
         return pb_sqdist(ctx, dtype, n, v, f->b, grad_out);
       case PB_F_LINEAR:
         if (grad_out != f->b && (rc = pb_copy(ctx, grad_out, f->b, (size_t)n * (dtype == PB_F32 ? 4 : 8)))) return rc;
+        if (lazy_value) return PB_OK;      // value computed once for the final state (see run())
         return pb_dot(ctx, dtype, n, f->b, v);
       default:
         pb_set_error("pb_solve: unknown smooth term %d", f->kind);
@@ -192,8 +200,15 @@ struct Solver {
     return eval_f(v, scratch);
   }
   int step(const void* xin, const void* gr, void* zout, bool extrap, R beta) {
-    if (extrap) return pb_ffb_step(ctx, dtype, n, xin, gr, z_prev, (double)gamma, (double)beta, g, nullptr, zout, nullptr, x_next);
-    return pb_fb_step(ctx, dtype, n, xin, gr, (double)gamma, g, nullptr, zout, nullptr);
+    const bool timed = profile && n_step_events < kMaxStepEvents;
+    if (timed) cudaEventRecord(ev_step[2 * n_step_events], ctx->stream);
+    const int rc = extrap ? pb_ffb_step(ctx, dtype, n, xin, gr, z_prev, (double)gamma, (double)beta, g, nullptr, zout, nullptr, x_next)
+                          : pb_fb_step(ctx, dtype, n, xin, gr, (double)gamma, g, nullptr, zout, nullptr);
+    if (timed) {
+      cudaEventRecord(ev_step[2 * n_step_events + 1], ctx->stream);
+      ++n_step_events;
+    }
+    return rc;
   }
   bool stop() const {                    // norm(res, Inf)/gamma <= tol
     const R rn = (R)sc.res_inf;
@@ -233,6 +248,46 @@ struct Solver {
     const bool adaptive = o->adaptive != 0;
     backtracks = 0;
     warned = 0;
+    lazy_value = f->kind == PB_F_LINEAR && !adaptive && o->gamma > 0;
+    profile = o->profile != 0;
+    ev_step = nullptr;
+    n_step_events = 0;
+    if (profile) {
+      ev_step = new cudaEvent_t[2 * kMaxStepEvents];
+      const int64_t want = o->maxit < kMaxStepEvents ? o->maxit : kMaxStepEvents;
+      for (int64_t i = 0; i < 2 * want; ++i) cudaEventCreate(&ev_step[i]);
+      cudaEventCreate(&ev_loop[0]);
+      cudaEventCreate(&ev_loop[1]);
+      cudaEventRecord(ev_loop[0], ctx->stream);
+    }
+    rc = run_loop(out);
+    if (profile) {
+      if (rc == PB_OK) {
+        cudaEventSynchronize(ev_loop[1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_loop[0], ev_loop[1]);
+        out->loop_ms = ms;
+        double tot = 0.0;
+        for (int i = 0; i < n_step_events; ++i) {
+          cudaEventElapsedTime(&ms, ev_step[2 * i], ev_step[2 * i + 1]);
+          tot += ms;
+        }
+        out->step_kernel_ms = tot;
+        out->step_kernel_launches = n_step_events;
+      }
+      const int64_t want = o->maxit < kMaxStepEvents ? o->maxit : kMaxStepEvents;
+      for (int64_t i = 0; i < 2 * want; ++i) cudaEventDestroy(ev_step[i]);
+      cudaEventDestroy(ev_loop[0]);
+      cudaEventDestroy(ev_loop[1]);
+      delete[] ev_step;
+    }
+    return rc;
+  }
+
+  int run_loop(pb_solve_result* out) {
+    int rc;
+    const bool fast = o->algorithm == PB_ALG_FFB;
+    const bool adaptive = o->adaptive != 0;
     // ---- init: forward_backward.jl:65-84 / fast_forward_backward.jl:73-97 ----
     if ((rc = eval_f(x, grad))) return rc;
     bool fx_pending = true;
@@ -313,6 +368,13 @@ struct Solver {
         f_x = f_value(sc);
         g_z = g_value(sc);
       }
+    }
+    if (profile) cudaEventRecord(ev_loop[1], ctx->stream);     // the K iterations end here
+    if (lazy_value) {                    // f(x) of the final state (LinearFunction: <c, x>)
+      if ((rc = pb_dot(ctx, dtype, n, f->b, x))) return rc;
+      Comb c;
+      if ((rc = read_comb(ctx, &c))) return rc;
+      f_x = f_value(c);
     }
     out->iterations = k;
     out->gamma = (double)gamma;
