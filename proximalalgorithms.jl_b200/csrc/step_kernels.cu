@@ -27,8 +27,30 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
   Acc<3, 1> acc;
   acc.clear();
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t base = tile * TILE + (int64_t)threadIdx.x * VEC;
+  // one 16-byte pack: compute, store, accumulate
+  auto do_pack = [&](int64_t i, const Pack<T, VEC>& xq, const Pack<T, VEC>& gq, const Pack<T, VEC>& zq) {
+    Pack<T, VEC> lo, hi, yv, zn, rv, xn;
+    if (PROX == PB_PROX_BOX && lov) lo = ld_pack<T, VEC, false>(lov + i);
+    if (PROX == PB_PROX_BOX && hiv) hi = ld_pack<T, VEC, false>(hiv + i);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const T l = (PROX == PB_PROX_BOX && lov) ? lo.v[e] : pa;
+      const T h = (PROX == PB_PROX_BOX && hiv) ? hi.v[e] : pb;
+      StepElem<T, PROX, EXTRAP>::template run<COMP>(xq.v[e], gq.v[e], EXTRAP ? zq.v[e] : T(0), l, h, gamma, beta, yv.v[e],
+                                                    zn.v[e], rv.v[e], xn.v[e], acc);
+    }
+    st_pack<T, VEC, HINT>(zo + i, zn);
+    if constexpr (EXTRAP) st_pack<T, VEC, HINT>(xo + i, xn);
+    if (yo) st_pack<T, VEC, HINT>(yo + i, yv);
+    if (ro) st_pack<T, VEC, HINT>(ro + i, rv);
+  };
+
+  // Balanced schedule: `rounds` full rounds in which EVERY CTA streams one TILE (UNROLL packs per thread in flight), then
+  // the remaining < gridDim.x tiles are shared by all CTAs at pack granularity, so no CTA works a whole tile longer than
+  // the others (at 1.25e7 elements per GPU -- n = 1e8 on 8 GPUs -- that imbalance was 0.7 of 10.3 tiles).
+  const int64_t rounds = ntiles / gridDim.x;
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t base = (r * gridDim.x + blockIdx.x) * TILE + (int64_t)threadIdx.x * VEC;
     Pack<T, VEC> xv[UNROLL], gv[UNROLL], zv[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -38,26 +60,19 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
       if constexpr (EXTRAP) zv[u] = ld_pack<T, VEC, HINT>(zp + i);
     }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int64_t i = base + (int64_t)u * PB_BLOCK * VEC;
-      Pack<T, VEC> lo, hi, yv, zn, rv, xn;
-      if (PROX == PB_PROX_BOX && lov) lo = ld_pack<T, VEC, false>(lov + i);
-      if (PROX == PB_PROX_BOX && hiv) hi = ld_pack<T, VEC, false>(hiv + i);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const T l = (PROX == PB_PROX_BOX && lov) ? lo.v[e] : pa;
-        const T h = (PROX == PB_PROX_BOX && hiv) ? hi.v[e] : pb;
-        StepElem<T, PROX, EXTRAP>::template run<COMP>(xv[u].v[e], gv[u].v[e], EXTRAP ? zv[u].v[e] : T(0), l, h, gamma,
-                                                      beta, yv.v[e], zn.v[e], rv.v[e], xn.v[e], acc);
-      }
-      st_pack<T, VEC, HINT>(zo + i, zn);
-      if constexpr (EXTRAP) st_pack<T, VEC, HINT>(xo + i, xn);
-      if (yo) st_pack<T, VEC, HINT>(yo + i, yv);
-      if (ro) st_pack<T, VEC, HINT>(ro + i, rv);
-    }
+    for (int u = 0; u < UNROLL; ++u) do_pack(base + (int64_t)u * PB_BLOCK * VEC, xv[u], gv[u], zv[u]);
   }
-  // ragged tail (< TILE elements), element-wise
-  for (int64_t i = ntiles * TILE + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * PB_BLOCK) {
+  const int64_t rem_start = rounds * gridDim.x * TILE;
+  const int64_t rem_packs = (n - rem_start) / VEC;
+  for (int64_t q = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; q < rem_packs; q += (int64_t)gridDim.x * PB_BLOCK) {
+    const int64_t i = rem_start + q * VEC;
+    Pack<T, VEC> xq = ld_pack<T, VEC, HINT>(x + i), gq = ld_pack<T, VEC, HINT>(g + i), zq;
+    if constexpr (EXTRAP) zq = ld_pack<T, VEC, HINT>(zp + i);
+    do_pack(i, xq, gq, zq);
+  }
+  // ragged tail (< VEC elements), element-wise
+  for (int64_t i = rem_start + rem_packs * VEC + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * PB_BLOCK) {
     const T l = (PROX == PB_PROX_BOX && lov) ? lov[i] : pa;
     const T h = (PROX == PB_PROX_BOX && hiv) ? hiv[i] : pb;
     T yv, zn, rv, xn;
