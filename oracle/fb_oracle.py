@@ -78,6 +78,8 @@ class LeastSquares:
     """f(x) = 0.5*||A x - b||^2 with the benchmark's explicit gradient (benchmark/benchmarks.jl:11-17):
     `res = A*x - b; (norm(res)^2/2, A'*res)` -- the gradient is a fresh array every call."""
 
+    is_generalized_quadratic = True   # ProximalOperators' trait for LeastSquares (read by panoc.jl:217)
+
     def __init__(self, A, b):
         self.A = np.asfortranarray(A)
         self.b = np.ascontiguousarray(b)

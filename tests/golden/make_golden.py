@@ -12,6 +12,8 @@ Sources (all paths relative to /root/reference):
   * test/problems/test_lasso_small.jl:17-23,42  -- literal 4x5 A, b and x_star.
   * test/problems/test_lasso_small_strongly_convex.jl:11-44,53 -- literal w, B, x_star; A = Q D Q',
     b = A x* + lam inv(A') sign(x*), x0 = A \\ b are re-derived with LAPACK exactly as the test does.
+  * test/accel/test_lbfgs.jl:6-101 -- literal Q, q, xs and the five reference L-BFGS directions.
+  * test/problems/test_sparse_logistic_small.jl:34 -- literal x_star.
 The literals are parsed out of the .jl files with regular expressions (nothing is copied by hand).
 """
 import hashlib
@@ -96,6 +98,28 @@ def unit_lasso_sc_5x5():
     return dict(A=np.asfortranarray(a), b=b, xstar=xs, x0=x0, lam=np.float64(lam), mf=np.float64(mf), Lf=np.float64(lf))
 
 
+def lbfgs_known_answers():
+    """test/accel/test_lbfgs.jl:6-101: Q (10x10), q, the five points xs and the five reference directions (memory 3)."""
+    src = open(os.path.join(REF, "test", "accel", "test_lbfgs.jl")).read()
+    qm = _matrix(_block_after(src, "Q = T["))
+    qv = _vector(_block_after(src, "q = T["))
+    i = src.index("xs = [")
+    j = src.index("dirs_ref = [")
+    k = src.index("@testset \"Arrays\"")
+    xs = np.array([_vector(b) for b in re.findall(r"T\[(.*?)\]", src[i:j], flags=re.S)])
+    dirs = np.array([_vector(b) for b in re.findall(r"T\[(.*?)\]", src[j:k], flags=re.S)])
+    assert qm.shape == (10, 10) and qv.shape == (10,) and xs.shape == (5, 10) and dirs.shape == (5, 10)
+    return dict(Q=qm, q=qv, xs=xs, dirs_ref=dirs)
+
+
+def unit_sparse_logistic():
+    """test/problems/test_sparse_logistic_small.jl:34 literal x_star (A, b are those of the 4x5 Lasso; lam = 0.1)."""
+    src = open(os.path.join(REF, "test", "problems", "test_sparse_logistic_small.jl")).read()
+    xs = _vector(_block_after(src, "x_star = T["))
+    assert xs.shape == (5,)
+    return dict(xstar=xs, lam=np.float64(0.1))
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not present: golden fixtures can only be regenerated in the build container")
@@ -106,6 +130,8 @@ def main():
         print(f"lasso_{name}: A{d['A'].shape} lam={d['lam']} obj(x*)={0.5 * r @ r + d['lam'] * np.abs(d['xstar']).sum():.16g}")
     np.savez_compressed(os.path.join(OUT, "unit_lasso_4x5.npz"), **unit_lasso_4x5())
     np.savez_compressed(os.path.join(OUT, "unit_lasso_sc_5x5.npz"), **unit_lasso_sc_5x5())
+    np.savez_compressed(os.path.join(OUT, "lbfgs_known_answers.npz"), **lbfgs_known_answers())
+    np.savez_compressed(os.path.join(OUT, "unit_sparse_logistic.npz"), **unit_sparse_logistic())
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 
