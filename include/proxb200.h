@@ -52,15 +52,18 @@ enum {
   PB_PROX_L1 = 1,      /* NormL1(lambda): soft threshold, value lambda*||z||_1   (BM:52,60)               */
   PB_PROX_BOX = 2,     /* IndBox(lo,hi): clamp, value 0  (test/problems/test_nonconvex_qp.jl:19,33)       */
   PB_PROX_SCALE = 3,   /* z = s*y with a caller-supplied factor: phase 2 of IndBallL2 (s = min(1, r/||y||)) */
-  PB_PROX_L21 = 4      /* NormL21(lambda, dim=1) on contiguous groups of `group` elements                  */
+  PB_PROX_L21 = 4,     /* NormL21(lambda, dim=1) on contiguous groups of `group` elements                  */
+  PB_PROX_SQRL2 = 5    /* Translate(SqrNormL2(lambda), -b): f = lambda/2*||x - b||^2, b = v0 or 0
+                          (test/problems/test_lasso_small.jl:38); prox z = (y - b)/(1 + gamma*lambda) + b           */
 };
 
 typedef struct pb_prox {
   int32_t kind;        /* PB_PROX_*                                                                        */
   int32_t group;       /* PB_PROX_L21: group length (elements); otherwise ignored                          */
-  double p0;           /* L1/L21: lambda;  BOX: lo (used when v0 == NULL);  SCALE: s                        */
+  double p0;           /* L1/L21/SQRL2: lambda;  BOX: lo (used when v0 == NULL);  SCALE: s                  */
   double p1;           /* BOX: hi (used when v1 == NULL)                                                   */
-  const void* v0;      /* BOX: optional per-element lower bounds (device, same dtype as the vectors)        */
+  const void* v0;      /* BOX: optional per-element lower bounds (device, same dtype as the vectors);
+                          SQRL2: optional translation vector b                                              */
   const void* v1;      /* BOX: optional per-element upper bounds                                            */
 } pb_prox;
 
@@ -77,6 +80,8 @@ enum {
   PB_S_AUX = 8,       /* [8],[9]  kernel-specific sum: ||y||^2 (pb_forward), ||v||^2 (pb_nrm2sq), <a,b> (pb_dot),
                                   ||A x - b||^2 (pb_lsq_*_residual), ||x - b||^2 (pb_sqdist)                        */
   PB_S_AUXINF = 10,   /* [10]     kernel-specific max: max|v_i| (pb_norm_inf)                                       */
+  PB_S_AUX2 = 12,     /* [12],[13] <s,y> of pb_lbfgs_update (own slots: the update can be enqueued behind a fused step   */
+  PB_S_AUX3 = 14,     /* [14],[15] <y,y> of pb_lbfgs_update  and an f evaluation and read back in ONE exchange)          */
   PB_NSCALARS = 16
 };
 
@@ -185,6 +190,37 @@ int pb_lsq_blockdiag_gradient(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, 
                               const void* r, void* grad);
 /* SquaredDistance (BM:19-28): grad = x - b, AUX = ||x - b||^2. */
 int pb_sqdist(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* b, void* grad);
+
+/* ---- K7: L-BFGS directions and the vector algebra of PANOC's line search ------------------------------------------
+ * (src/accel/lbfgs.jl, src/algorithms/panoc.jl; abbreviated LB, PN below).  Single GPU: the two-loop recursion keeps its
+ * coefficients on the device (no host round trip between its 2m+1 launches), which needs un-sharded dot products. */
+int pb_lincomb2(pb_ctx* ctx, int dtype, int64_t n, double a, const void* x, double b, const void* y,
+                void* out);                               /* out = a.*x .+ b.*y  (PN:183-184, :214-215, :234-237) */
+int pb_scale(pb_ctx* ctx, int dtype, int64_t n, double s, const void* x, void* out);   /* out = s.*x  (PN:116,120) */
+
+typedef struct pb_lbfgs pb_lbfgs;          /* LBFGSOperator{M} (LB:5-28): ring of M (+1 spare) pairs on the device */
+int pb_lbfgs_create(pb_ctx* ctx, int dtype, int64_t n, int mem, pb_lbfgs** out);        /* initialize, LB:102-104 */
+int pb_lbfgs_destroy(pb_lbfgs* op);
+int pb_lbfgs_reset(pb_lbfgs* op);                                                       /* reset!, LB:53-56      */
+int pb_lbfgs_info(const pb_lbfgs* op, int* currmem, int* curridx, double* H);
+int pb_lbfgs_pair(const pb_lbfgs* op, int pos, void** s, void** y, double* ys);        /* ring position 1..M    */
+/* update!(L, s, y) (LB:30-51) fused with PANOC's differences (PN:125-126): s = a - a_prev, y = b - b_prev (a NULL
+ * "prev" means s = a / y = b) are written into the ring's spare slot in one pass with AUX2 = <s,y>, AUX3 = <y,y>.
+ * Asynchronous.  The caller reads the two sums with its per-iteration exchange and calls pb_lbfgs_commit, which does
+ * the `if ys > 0` bookkeeping (LB:34-48) in the element type. */
+int pb_lbfgs_update(pb_ctx* ctx, pb_lbfgs* op, const void* a, const void* a_prev, const void* b, const void* b_prev);
+int pb_lbfgs_commit(pb_lbfgs* op, double ys, double yty, int* accepted);
+/* mul!(d, L, v) (LB:66-95) followed by d .*= scale (PN:116 uses -1), and optionally x_d = x + d (PN:183) in the last
+ * launch (x, x_d both NULL to skip).  d may alias v.  Asynchronous: 2*currmem + 2 launches, no host read-back. */
+int pb_lbfgs_apply(pb_ctx* ctx, pb_lbfgs* op, const void* v, double scale, void* d, const void* x, void* x_d);
+
+/* ---- K8: fused Douglas-Rachford iteration (src/algorithms/douglas_rachford.jl:54-63) -----------------------------
+ * y = prox_{gamma f}(x); r = 2y - x; z = prox_{gamma g}(r); res = y - z; x_out = x - res in ONE pass, with RESINF =
+ * norm(res, Inf) (stop rule, :65-69) and RESSQ = ||res||^2.  f and g must be element-wise kinds (ZERO, L1, BOX, SQRL2);
+ * PB_EUNSUPPORTED otherwise.  x_out may alias x.  y, r, z, res are optional outputs (NULL = not materialised).
+ * Algorithmic traffic: 2 vectors (read x, write x_out), +1 for the data vector of SQRL2. */
+int pb_dr_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, double gamma, const pb_prox* f, const pb_prox* g,
+               void* x_out, void* y, void* r, void* z, void* res);
 
 /* ---- native driver loop ---------------------------------------------------------------------------------------------
  * The reference's IterativeAlgorithm loop (src/ProximalAlgorithms.jl:114-123) around ForwardBackward / FastForwardBackward

@@ -12,10 +12,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libproxb200.so")
 
 PB_F32, PB_F64 = 0, 1
-PB_PROX_ZERO, PB_PROX_L1, PB_PROX_BOX, PB_PROX_SCALE, PB_PROX_L21 = 0, 1, 2, 3, 4
+PB_PROX_ZERO, PB_PROX_L1, PB_PROX_BOX, PB_PROX_SCALE, PB_PROX_L21, PB_PROX_SQRL2 = 0, 1, 2, 3, 4, 5
 PB_OPT_CTAS_PER_SM, PB_OPT_STREAM_HINTS, PB_OPT_UNROLL, PB_OPT_STEP_IMPL, PB_OPT_FUSED_EXCHANGE = 0, 1, 2, 3, 4
 PB_IPC_HANDLE_BYTES, PB_MAX_WORLD = 64, 8
-PB_S_GSUM, PB_S_RESSQ, PB_S_GDR, PB_S_RESINF, PB_S_AUX, PB_S_AUXINF, PB_NSCALARS = 0, 2, 4, 6, 8, 10, 16
+PB_S_GSUM, PB_S_RESSQ, PB_S_GDR, PB_S_RESINF, PB_S_AUX, PB_S_AUXINF, PB_S_AUX2, PB_S_AUX3, PB_NSCALARS = 0, 2, 4, 6, 8, 10, 12, 14, 16
 
 
 class ProxB200Error(RuntimeError):
@@ -100,6 +100,17 @@ SIGNATURES = {
     "pb_lsq_blockdiag_residual": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "pb_lsq_blockdiag_gradient": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp]),
     "pb_sqdist": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "pb_lincomb2": (_i, [_vp, _i, _i64, _d, _vp, _d, _vp, _vp]),
+    "pb_scale": (_i, [_vp, _i, _i64, _d, _vp, _vp]),
+    "pb_lbfgs_create": (_i, [_vp, _i, _i64, _i, C.POINTER(_vp)]),
+    "pb_lbfgs_destroy": (_i, [_vp]),
+    "pb_lbfgs_reset": (_i, [_vp]),
+    "pb_lbfgs_info": (_i, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "pb_lbfgs_pair": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_double)]),
+    "pb_lbfgs_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "pb_lbfgs_commit": (_i, [_vp, _d, _d, C.POINTER(C.c_int)]),
+    "pb_lbfgs_apply": (_i, [_vp, _vp, _vp, _d, _vp, _vp, _vp]),
+    "pb_dr_step": (_i, [_vp, _i, _i64, _vp, _d, _pp, _pp, _vp, _vp, _vp, _vp, _vp]),
     "pb_solve": (_i, [_vp, _i, _i64, C.POINTER(pb_smooth), _pp, C.POINTER(pb_solve_opts), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                       C.POINTER(pb_solve_result)]),
     "pb_ffb_step_host": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _d, _d, _pp, _vp, _vp, C.POINTER(C.c_double)]),

@@ -87,18 +87,18 @@ class _Engine:
         return self.eval_f(f, x, grad_scratch)
 
     # ---- K1 / K2 -------------------------------------------------------------------------------------------------
-    def fb_step(self, R, g, x, grad, gamma, z, z_prev=None, beta=None, x_next=None, y_scratch=None):
+    def fb_step(self, R, g, x, grad, gamma, z, z_prev=None, beta=None, x_next=None, y_scratch=None, res_out=None):
         """Enqueue y = x - gamma*grad, z = prox(y), res = x - z (+ optional x_next = z + beta*(z - z_prev)).
-        Returns `g_of(scalars)` -> g(z)."""
+        `res_out`: materialise res (the line-search methods keep it as a state vector).  Returns `g_of(scalars)` -> g(z)."""
         lib, ctx, dt, n = self.lib, self.ctx, pb_dtype(R), x.numel()
         extrap = x_next is not None
         if getattr(g, "fused", False):
             d = g.descriptor(R)
             if extrap:
                 L.check(lib.pb_ffb_step(ctx.h, dt, n, ptr(x), ptr(grad), ptr(z_prev), float(gamma), float(beta), C.byref(d),
-                                        None, ptr(z), None, ptr(x_next)))
+                                        None, ptr(z), ptr(res_out), ptr(x_next)))
             else:
-                L.check(lib.pb_fb_step(ctx.h, dt, n, ptr(x), ptr(grad), float(gamma), C.byref(d), None, ptr(z), None))
+                L.check(lib.pb_fb_step(ctx.h, dt, n, ptr(x), ptr(grad), float(gamma), C.byref(d), None, ptr(z), ptr(res_out)))
             return lambda sc: g.value_from(R, sc.gsum)
         if isinstance(g, IndBallL2):
             # phase 1: y and ||y||^2 (combined over shards); phase 2: fused step with the scale factor
@@ -107,14 +107,14 @@ class _Engine:
             d = g.scale_descriptor(R, sc.aux)
             if extrap:
                 L.check(lib.pb_ffb_step(ctx.h, dt, n, ptr(x), ptr(grad), ptr(z_prev), float(gamma), float(beta), C.byref(d),
-                                        None, ptr(z), None, ptr(x_next)))
+                                        None, ptr(z), ptr(res_out), ptr(x_next)))
             else:
-                L.check(lib.pb_fb_step(ctx.h, dt, n, ptr(x), ptr(grad), float(gamma), C.byref(d), None, ptr(z), None))
+                L.check(lib.pb_fb_step(ctx.h, dt, n, ptr(x), ptr(grad), float(gamma), C.byref(d), None, ptr(z), ptr(res_out)))
             return lambda sc_: R(0)
         # user-supplied proximable term: the reference's unfused sequence with its prox! callback in the middle
         L.check(lib.pb_forward(ctx.h, dt, n, ptr(x), ptr(grad), float(gamma), ptr(y_scratch)))
         g_z = g.prox_(z, y_scratch, R(gamma))
-        L.check(lib.pb_residual(ctx.h, dt, n, ptr(x), ptr(z), ptr(grad), None))
+        L.check(lib.pb_residual(ctx.h, dt, n, ptr(x), ptr(z), ptr(grad), ptr(res_out)))
         if extrap:
             L.check(lib.pb_extrapolate(ctx.h, dt, n, ptr(z), ptr(z_prev), float(beta), ptr(x_next)))
         return lambda sc_: R(g_z)
@@ -464,6 +464,8 @@ def _native_solve(alg, it):
     """Run the whole solve in `pb_solve` if possible; returns (solution, iterations) or None."""
     from .host import DeviceExchangeComm
 
+    if type(it) not in (ForwardBackwardIteration, FastForwardBackwardIteration):
+        return None           # pb_solve implements the two forward-backward loops only
     tol = getattr(alg.stop, "_default_tol", None)
     if tol is None or alg.solution is not default_solution or alg.verbose:
         return None

@@ -16,17 +16,22 @@ from .algorithms import (  # noqa: F401
     default_solution,
     default_stopping_criterion,
 )
+from .accel import LBFGS, LBFGSOperator, NoAcceleration  # noqa: F401
+from .douglas_rachford import DouglasRachford, DouglasRachfordIteration, DouglasRachfordState  # noqa: F401
 from .functions import (  # noqa: F401
     BlockDiagLeastSquares,
     IndBallL2,
     IndBox,
     LeastSquares,
     LinearFunction,
+    MatrixOp,
     NormL1,
     NormL21,
+    SqrNormL2,
     SquaredDistance,
     Zero,
 )
+from .panoc import PANOC, PANOCIteration, PANOCState  # noqa: F401
 from .host import Context, DeviceExchangeComm, LocalComm, Scalars, TorchDistComm, shard_bounds  # noqa: F401
 from .nesterov import (  # noqa: F401
     AdaptiveNesterovSequence,

@@ -1,0 +1,218 @@
+// dr_kernels.cu -- K8: fused Douglas-Rachford iteration (src/algorithms/douglas_rachford.jl:54-63) for element-wise prox pairs.
+//
+//   y = prox_{gamma f}(x);  r = 2y - x;  z = prox_{gamma g}(r);  res = y - z;  x <- x - res;   stop on norm(res, Inf)/gamma
+//
+// The reference makes five passes over six vectors (prox!, broadcast, prox!, broadcast, broadcast, norm: 13 vector
+// reads/writes per element).  Here the whole iteration is ONE pass: read x (+ the data vector b of a translated
+// quadratic), write x; y, r, z, res are only materialised on request (lazy state fields / the final solution), and
+// norm(res, Inf), ||res||^2 come out of the same pass.  Algorithmic traffic: 2 vectors per iteration (3 with b).
+// HBM-bound streaming kernel, no tensor-core formulation exists.
+#include "step_common.cuh"
+
+struct DrProx {
+  int kind;            // PB_PROX_ZERO / L1 / BOX / SQRL2
+  double a, b;         // L1: gl = gamma*lambda.  BOX: lo, hi.  SQRL2: den = 1 + gamma*lambda (all in the element type)
+  const void* v0;      // BOX: per-element lo;  SQRL2: translation vector b (f(x) = lambda/2 ||x - b||^2), may be NULL
+  const void* v1;      // BOX: per-element hi
+};
+
+struct DrParams {
+  const void* x;
+  void* x_out;
+  void *y, *r, *z, *res;   // optional outputs
+  int64_t n;
+  DrProx f, g;
+  PbWorkspace* ws;
+  double* outs;
+  XchgParams xchg;
+};
+
+template <typename T>
+__device__ __forceinline__ T dr_prox(const DrProx& p, T v, int64_t i) {
+  switch (p.kind) {
+    case PB_PROX_L1:
+      return prox_elem<T, PB_PROX_L1>(v, (T)p.a, T(0));
+    case PB_PROX_BOX: {
+      const T lo = p.v0 ? static_cast<const T*>(p.v0)[i] : (T)p.a;
+      const T hi = p.v1 ? static_cast<const T*>(p.v1)[i] : (T)p.b;
+      return prox_elem<T, PB_PROX_BOX>(v, lo, hi);
+    }
+    case PB_PROX_SQRL2: {
+      // Translate(SqrNormL2(lambda), -b): w = v - b; w / (1 + gamma*lambda); + b   (three separately rounded operations)
+      if (p.v0) {
+        const T bb = static_cast<const T*>(p.v0)[i];
+        return add_rn(sub_rn(v, bb) / (T)p.a, bb);
+      }
+      return v / (T)p.a;
+    }
+    default:
+      return v;
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(PB_BLOCK) k_dr_step(DrParams p) {
+  constexpr bool COMP = sizeof(T) == 8;
+  const T* __restrict__ x = static_cast<const T*>(p.x);
+  T* __restrict__ xo = static_cast<T*>(p.x_out);
+  T* __restrict__ yo = static_cast<T*>(p.y);
+  T* __restrict__ ro = static_cast<T*>(p.r);
+  T* __restrict__ zo = static_cast<T*>(p.z);
+  T* __restrict__ so = static_cast<T*>(p.res);
+  Acc<1, 1> acc;
+  acc.clear();
+  auto elem = [&](T xv, int64_t i, T& y, T& r, T& z, T& res, T& xn) {
+    y = dr_prox<T>(p.f, xv, i);                      // :58
+    r = sub_rn(mul_rn(T(2), y), xv);                 // :59
+    z = dr_prox<T>(p.g, r, i);                       // :60
+    res = sub_rn(y, z);                              // :61
+    xn = sub_rn(xv, res);                            // :62
+    const double rd = (double)res;
+    if (COMP)
+      dd_add_prod(acc.s[0], rd, rd);
+    else
+      acc.s[0].hi = __fma_rn(rd, rd, acc.s[0].hi);
+    acc.m[0] = nanmax(acc.m[0], fabs(rd));
+  };
+  const int64_t npacks = p.n / VEC;
+  for (int64_t q = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; q < npacks; q += (int64_t)gridDim.x * PB_BLOCK) {
+    const int64_t i = q * VEC;
+    Pack<T, VEC> xv = ld_pack<T, VEC, true>(x + i), y, r, z, res, xn;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) elem(xv.v[e], i + e, y.v[e], r.v[e], z.v[e], res.v[e], xn.v[e]);
+    st_pack<T, VEC, true>(xo + i, xn);
+    if (yo) st_pack<T, VEC, true>(yo + i, y);
+    if (ro) st_pack<T, VEC, true>(ro + i, r);
+    if (zo) st_pack<T, VEC, true>(zo + i, z);
+    if (so) st_pack<T, VEC, true>(so + i, res);
+  }
+  for (int64_t i = npacks * VEC + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * PB_BLOCK) {
+    T y, r, z, res, xn;
+    elem(x[i], i, y, r, z, res, xn);
+    xo[i] = xn;
+    if (yo) yo[i] = y;
+    if (ro) ro[i] = r;
+    if (zo) zo[i] = z;
+    if (so) so[i] = res;
+  }
+  OutMap map;
+  map.sum_slot[0] = PB_S_RESSQ;
+  map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
+  map.max_slot[0] = PB_S_RESINF;
+  map.max_slot[1] = -1;
+  grid_reduce<1, 1, PB_BLOCK>(acc, p.ws, p.outs, map, &p.xchg);
+}
+
+// prox parameters in the element type, combined on the host with one rounding each (like the package does)
+template <typename T>
+static int dr_fill(DrProx* d, const pb_prox* g, double gamma) {
+  d->kind = g->kind;
+  d->a = d->b = 0.0;
+  d->v0 = d->v1 = nullptr;
+  switch (g->kind) {
+    case PB_PROX_ZERO:
+      return PB_OK;
+    case PB_PROX_L1:
+      d->a = (double)mul_rn_host((T)gamma, (T)g->p0);
+      return PB_OK;
+    case PB_PROX_BOX:
+      d->a = g->p0;
+      d->b = g->p1;
+      d->v0 = g->v0;
+      d->v1 = g->v1;
+      return PB_OK;
+    case PB_PROX_SQRL2: {
+      const T gl = mul_rn_host((T)gamma, (T)g->p0);
+      volatile T den = T(1) + gl;
+      d->a = (double)den;
+      d->v0 = g->v0;
+      return PB_OK;
+    }
+    default:
+      pb_set_error("pb_dr_step: prox kind %d is not element-wise (use the unfused sequence)", g->kind);
+      return PB_EUNSUPPORTED;
+  }
+}
+
+extern "C" int pb_dr_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, double gamma, const pb_prox* f, const pb_prox* g,
+                          void* x_out, void* y, void* r, void* z, void* res) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  PB_REQUIRE(n >= 0, "negative length");
+  PB_REQUIRE(f != nullptr && g != nullptr, "null prox descriptor");
+  PB_REQUIRE(n == 0 || (x && x_out), "null vector");
+  DrParams p;
+  p.x = x;
+  p.x_out = x_out;
+  p.y = y;
+  p.r = r;
+  p.z = z;
+  p.res = res;
+  p.n = n;
+  int rc = dtype == PB_F32 ? dr_fill<float>(&p.f, f, gamma) : dr_fill<double>(&p.f, f, gamma);
+  if (rc != PB_OK) return rc;
+  rc = dtype == PB_F32 ? dr_fill<float>(&p.g, g, gamma) : dr_fill<double>(&p.g, g, gamma);
+  if (rc != PB_OK) return rc;
+  p.ws = ctx->ws;
+  p.outs = ctx->scalars_dev;
+  pb_xchg_next(ctx, &p.xchg, ctx->xchg_fused != 0 && n > 0);
+  const void* ptrs[] = {x, x_out, y, r, z, res, p.f.v0, p.f.v1, p.g.v0, p.g.v1};
+  bool vec_ok = true;
+  for (const void* q : ptrs) vec_ok = vec_ok && (!q || pb_aligned16(q));
+  if (dtype == PB_F32) {
+    if (vec_ok)
+      k_dr_step<float, 4><<<pb_stream_grid(ctx, PB_BLOCK * 4 * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+    else
+      k_dr_step<float, 1><<<pb_stream_grid(ctx, PB_BLOCK * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+  } else {
+    if (vec_ok)
+      k_dr_step<double, 2><<<pb_stream_grid(ctx, PB_BLOCK * 2 * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+    else
+      k_dr_step<double, 1><<<pb_stream_grid(ctx, PB_BLOCK * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+  }
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}
+
+// standalone prox of the translated quadratic (pb_prox_apply dispatches here): z = (y - b)/(1 + gamma*lambda) + b,
+// GSUM = sum ((y - b)/(1 + gamma*lambda))^2, so that f(z) = lambda/2 * GSUM (ProximalOperators SqrNormL2 / Translate).
+template <typename T>
+__global__ void __launch_bounds__(PB_BLOCK) k_prox_sqrl2(const T* __restrict__ y, const T* __restrict__ b, T* __restrict__ z,
+                                                         int64_t n, double den_d, PbWorkspace* ws, double* outs) {
+  constexpr bool COMP = sizeof(T) == 8;
+  const T den = (T)den_d;
+  Acc<1, 0> acc;
+  acc.clear();
+  for (int64_t i = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * PB_BLOCK) {
+    const T w = b ? sub_rn(y[i], b[i]) / den : y[i] / den;
+    z[i] = b ? add_rn(w, b[i]) : w;
+    if (COMP)
+      dd_add_prod(acc.s[0], (double)w, (double)w);
+    else
+      acc.s[0].hi = __fma_rn((double)w, (double)w, acc.s[0].hi);
+  }
+  OutMap map;
+  map.sum_slot[0] = PB_S_GSUM;
+  map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
+  map.max_slot[0] = map.max_slot[1] = -1;
+  grid_reduce<1, 0, PB_BLOCK>(acc, ws, outs, map);
+}
+
+int pb_prox_sqrl2_apply(pb_ctx* ctx, int dtype, int64_t n, const void* y, double gamma, const pb_prox* g, void* z) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  PB_REQUIRE(n >= 0, "negative length");
+  PB_REQUIRE(n == 0 || (y && z), "null vector");
+  DrProx d;
+  const int rc = dtype == PB_F32 ? dr_fill<float>(&d, g, gamma) : dr_fill<double>(&d, g, gamma);
+  if (rc != PB_OK) return rc;
+  const int grid = pb_stream_grid(ctx, PB_BLOCK * 4, n, 4);
+  if (dtype == PB_F32)
+    k_prox_sqrl2<float><<<grid, PB_BLOCK, 0, ctx->stream>>>((const float*)y, (const float*)d.v0, (float*)z, n, d.a, ctx->ws,
+                                                             ctx->scalars_dev);
+  else
+    k_prox_sqrl2<double><<<grid, PB_BLOCK, 0, ctx->stream>>>((const double*)y, (const double*)d.v0, (double*)z, n, d.a, ctx->ws,
+                                                              ctx->scalars_dev);
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}

@@ -708,10 +708,14 @@ static int launch_ew(pb_ctx* ctx, int dtype, int64_t n, const void* a, const voi
   return dtype == PB_F32 ? launch_ew_t<float, OP>(ctx, p) : launch_ew_t<double, OP>(ctx, p);
 }
 
+int pb_prox_sqrl2_apply(pb_ctx* ctx, int dtype, int64_t n, const void* y, double gamma, const pb_prox* g, void* z);  // dr_kernels.cu
+
 extern "C" int pb_prox_apply(pb_ctx* ctx, int dtype, int64_t n, const void* y, double gamma, const pb_prox* g, void* z) {
   PB_REQUIRE(g != nullptr, "null prox descriptor");
   PB_REQUIRE(n == 0 || z != nullptr, "null output");
   switch (g->kind) {
+    case PB_PROX_SQRL2:
+      return pb_prox_sqrl2_apply(ctx, dtype, n, y, gamma, g, z);
     case PB_PROX_ZERO:
       return launch_ew<OP_COPY>(ctx, dtype, n, y, nullptr, nullptr, z, 0, 0, -1, -1);
     case PB_PROX_L1: {

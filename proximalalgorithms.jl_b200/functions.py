@@ -71,6 +71,41 @@ class Zero:
         return R(0)
 
 
+class MatrixOp:
+    """Dense linear map `A` of the composite problems f(Ax) + g(x) (panoc.jl:43; `A = I` is spelled `A=None`).
+    Column-major on the device; `A*x` and `A'*v` are the K4 GEMV kernels (the same ones LeastSquares uses)."""
+
+    def __init__(self, A, device=None):
+        t = torch()
+        ctx = Context.get(device)
+        self.ctx = ctx
+        if isinstance(A, t.Tensor):
+            self.R = real_type(A.dtype)
+            self.A_cm = A.to(ctx.device).t().contiguous()
+        else:
+            A = np.asarray(A)
+            self.R = real_type(A.dtype)
+            self.A_cm = t.as_tensor(np.ascontiguousarray(A.T)).to(ctx.device)
+        self.m, self.n = int(self.A_cm.shape[1]), int(self.A_cm.shape[0])
+        self.dtype = self.A_cm.dtype
+
+    def mul_into(self, out, x):
+        """out = A * x (also leaves ||A x||^2 in AUX)."""
+        check_vec(x, self.n, self.dtype)
+        check_vec(out, self.m, self.dtype)
+        ctx = self.ctx
+        L.check(ctx.lib.pb_lsq_dense_residual(ctx.h, pb_dtype(self.R), self.m, self.n, ptr(self.A_cm), self.m, ptr(x), None, ptr(out)))
+        return out
+
+    def mul_t_into(self, out, v):
+        """out = A' * v."""
+        check_vec(v, self.m, self.dtype)
+        check_vec(out, self.n, self.dtype)
+        ctx = self.ctx
+        L.check(ctx.lib.pb_lsq_dense_gradient(ctx.h, pb_dtype(self.R), self.m, self.n, ptr(self.A_cm), self.m, ptr(v), ptr(out)))
+        return out
+
+
 class LeastSquares:
     """f(x) = 0.5*||A x - b||^2 for a dense matrix, with the benchmark's explicit gradient
     `res = A*x - b; (norm(res)^2/2, A'*res)` (benchmark/benchmarks.jl:11-17).
@@ -79,6 +114,8 @@ class LeastSquares:
     (matching the row shard of x): the m-vector of partial products is all-gathered and folded in rank order
     (SURVEY.md section 8e), then `A_p' r` is local.
     """
+
+    is_generalized_quadratic = True      # ProximalOperators' trait of LeastSquares, read by panoc.jl:217
 
     def __init__(self, A, b, comm=None, device=None):
         t = torch()
@@ -147,6 +184,8 @@ class BlockDiagLeastSquares:
     BASELINE.json configs[1]; structure fixed by SURVEY.md section 7 hard part 6).  `blocks_cm` is a (B, nb, mb) tensor, i.e.
     every block column-major.  Sharding: whole blocks per rank, no vector collective; the value is summed with the
     scalar block."""
+
+    is_generalized_quadratic = True
 
     def __init__(self, blocks_cm, b, comm=None):
         t = torch()
@@ -252,13 +291,18 @@ class LinearFunction:
 class _FusedProx:
     fused = True
 
+    def prox_enqueue(self, ctx, z, y, gamma, comm=None):
+        """prox!(z, g, y, gamma) with the value left in the scalar block (GSUM): no host synchronisation."""
+        R = real_type(y.dtype)
+        d = self.descriptor(R)
+        L.check(ctx.lib.pb_prox_apply(ctx.h, pb_dtype(R), y.numel(), ptr(y), float(gamma), C.byref(d), ptr(z)))
+
     def prox_(self, z, y, gamma):
         """Reference-shaped in-place prox!(z, g, y, gamma) -> g(z) (standalone kernel K3)."""
         ctx = Context.get(y.device)
         R = real_type(y.dtype)
-        d = self.descriptor(R)
-        L.check(ctx.lib.pb_prox_apply(ctx.h, pb_dtype(R), y.numel(), ptr(y), float(gamma), C.byref(d), ptr(z)))
-        if self.kind in (L.PB_PROX_L1, L.PB_PROX_L21):
+        self.prox_enqueue(ctx, z, y, gamma)
+        if self.kind in (L.PB_PROX_L1, L.PB_PROX_L21, L.PB_PROX_SQRL2):
             row = ctx.read_scalars()
             return self.value_from(R, row[L.PB_S_GSUM] + row[L.PB_S_GSUM + 1])
         return R(0)
@@ -323,6 +367,55 @@ class NormL21(_FusedProx):
         return R(R(self.lam) * R(gsum))
 
 
+class SqrNormL2(_FusedProx):
+    """f(x) = lam/2 * ||x - b||^2: ProximalOperators' `Translate(SqrNormL2(lam), -b)` (test/problems/test_lasso_small.jl:38;
+    b=None is the plain SqrNormL2).  Both a smooth term (value_and_gradient) and an element-wise proximable term
+    (prox z = (y - b)/(1 + gamma*lam) + b), so it can sit on either side of a splitting."""
+
+    kind = L.PB_PROX_SQRL2
+    is_generalized_quadratic = True
+
+    def __init__(self, lam=1.0, b=None, device=None):
+        if lam < 0:
+            raise ValueError("parameter lambda must be nonnegative")
+        self.lam = lam
+        self.b = None
+        if b is not None:
+            ctx = Context.get(device if device is not None else (b.device if hasattr(b, "is_cuda") and b.is_cuda else None))
+            self.b = _as_device(b, ctx.device).contiguous()
+
+    def descriptor(self, R):
+        return L.pb_prox(L.PB_PROX_SQRL2, 0, float(R(self.lam)), 0.0, self.b.data_ptr() if self.b is not None else None, None)
+
+    def value_from(self, R, gsum):
+        return R(R(R(self.lam) / R(2)) * R(gsum))
+
+    def value_and_gradient_into(self, ctx, x, grad):
+        """grad = lam*(x - b), value = lam/2*||x - b||^2 (sqrt-then-square like `norm(.)^2`)."""
+        R = real_type(x.dtype)
+        dt, n = pb_dtype(R), x.numel()
+        if self.b is not None:
+            L.check(ctx.lib.pb_sqdist(ctx.h, dt, n, ptr(x), ptr(self.b), ptr(grad)))
+        else:
+            L.check(ctx.lib.pb_scale(ctx.h, dt, n, 1.0, ptr(x), ptr(grad)))
+            L.check(ctx.lib.pb_nrm2sq(ctx.h, dt, n, ptr(x)))
+        if float(R(self.lam)) != 1.0:
+            L.check(ctx.lib.pb_scale(ctx.h, dt, n, float(R(self.lam)), ptr(grad), ptr(grad)))
+        lam = R(self.lam)
+
+        def val(row, comb):
+            nr = R(np.sqrt(np.float64(comb.aux if comb is not None else row[L.PB_S_AUX] + row[L.PB_S_AUX + 1])))
+            return R(R(lam / R(2)) * R(nr * nr))
+
+        return Deferred(val)
+
+    def value_and_gradient(self, x):
+        ctx = Context.get(x.device)
+        grad = torch().empty_like(x)
+        val = self.value_and_gradient_into(ctx, x, grad)
+        return val.resolve(ctx.read_scalars(), None), grad
+
+
 class IndBallL2:
     """Indicator of {||x||_2 <= r}.  Two-phase prox (global norm, then scale): not single-pass fusable
     (SURVEY.md section 7 hard part 7).  Phase 1 = pb_forward / pb_nrm2sq (AUX = ||y||^2, combined across shards), phase 2 = the
@@ -344,14 +437,16 @@ class IndBallL2:
     def scale_descriptor(self, R, ysq):
         return L.pb_prox(L.PB_PROX_SCALE, 0, float(self.scale_factor(R, ysq)), 0.0, None, None)
 
-    def prox_(self, z, y, gamma, comm=None):
-        ctx = Context.get(y.device)
+    def prox_enqueue(self, ctx, z, y, gamma, comm=None):
         R = real_type(y.dtype)
         L.check(ctx.lib.pb_nrm2sq(ctx.h, pb_dtype(R), y.numel(), ptr(y)))
         sc = (comm or LocalComm()).exchange(ctx)
         d = self.scale_descriptor(R, sc.aux)
         L.check(ctx.lib.pb_prox_apply(ctx.h, pb_dtype(R), y.numel(), ptr(y), float(gamma), C.byref(d), ptr(z)))
-        return R(0)
+
+    def prox_(self, z, y, gamma, comm=None):
+        self.prox_enqueue(Context.get(y.device), z, y, gamma, comm=comm)
+        return real_type(y.dtype)(0)
 
     def value_from(self, R, gsum):
         return R(0)

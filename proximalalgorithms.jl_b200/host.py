@@ -73,7 +73,7 @@ def _nanmax(vals):
 class Scalars:
     """Host view of one (combined) scalar block.  Sums are rounded once from their double-double pairs."""
 
-    __slots__ = ("gsum", "res_sq", "gdr", "res_inf", "aux", "aux_inf", "parts")
+    __slots__ = ("gsum", "res_sq", "gdr", "res_inf", "aux", "aux_inf", "aux2", "aux3", "parts")
 
     def __init__(self, parts: np.ndarray):
         # parts: (P, PB_NSCALARS) -- one row per shard, in rank order
@@ -89,6 +89,8 @@ class Scalars:
         self.res_sq = s(L.PB_S_RESSQ)
         self.gdr = s(L.PB_S_GDR)
         self.aux = s(L.PB_S_AUX)
+        self.aux2 = s(L.PB_S_AUX2)
+        self.aux3 = s(L.PB_S_AUX3)
         self.res_inf = _nanmax(parts[:, L.PB_S_RESINF].tolist())
         self.aux_inf = _nanmax(parts[:, L.PB_S_AUXINF].tolist())
 

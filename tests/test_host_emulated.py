@@ -1,0 +1,180 @@
+"""CPU tests of the solvers' HOST logic (buffer renames, scalar arithmetic in R, line-search control flow) against the
+oracle, with the kernels replaced by the numpy emulation of the C ABI in tests/emu_lib.py.  The emulation is test
+infrastructure: the product has no CPU path and these tests do not claim kernel parity -- the `-m gpu` tests do that
+through the real library."""
+import numpy as np
+import pytest
+import torch
+
+import proxb200 as pa
+from oracle import fb_oracle as o
+from oracle import panoc_oracle as po
+from proxb200 import algorithms, functions, host
+
+from emu_lib import EmuContext
+
+TYPES = [np.float64, np.float32]
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    ctx = EmuContext()
+    monkeypatch.setattr(host.Context, "get", classmethod(lambda cls, device=None: ctx))
+
+    def check_vec(t_, n=None, dtype=None):
+        assert t_.is_contiguous() and t_.dim() == 1
+        assert n is None or t_.numel() == n
+        assert dtype is None or t_.dtype == dtype
+
+    for mod in (host, functions, algorithms):
+        monkeypatch.setattr(mod, "check_vec", check_vec)
+    from proxb200 import accel
+
+    monkeypatch.setattr(accel, "check_vec", check_vec)
+    return ctx
+
+
+def _lasso_4x5(golden, T):
+    d = golden("unit_lasso_4x5")
+    A, b = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T)
+    lam = T(T(0.1) * np.max(np.abs(A.T @ b)))
+    return A, b, lam, d["xstar"].astype(T)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_emulated_ffb_matches_oracle(emu, golden, T):
+    # sanity of the emulation itself on the already GPU-verified FB/FFB host code
+    A, b, lam, xstar = _lasso_4x5(golden, T)
+    for adaptive in (False, True):
+        kw = {} if adaptive else {"Lf": T(np.linalg.norm(A, 2) ** 2)}
+        z_o, it_o = o.fast_forward_backward(np.zeros(5, T), o.LeastSquares(A, b), o.NormL1(lam), tol=T(1e-4), **kw)
+        z, it = pa.FastForwardBackward(tol=T(1e-4), driver="python")(x0=np.zeros(5, T), f=pa.LeastSquares(A, b), g=pa.NormL1(lam), **kw)
+        assert abs(it - it_o) <= 1 and np.max(np.abs(z - z_o)) <= (1e-9 if T is np.float64 else 1e-4)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_lbfgs_operator_known_directions(emu, golden, T):
+    # test/accel/test_lbfgs.jl:103-131 through the product's LBFGSOperator wrapper
+    d = golden("lbfgs_known_answers")
+    Q, q, xs, dirs = (d[k].astype(T) for k in ("Q", "q", "xs", "dirs_ref"))
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a))   # noqa: E731
+    H = pa.LBFGS(3).initialize(dev(np.zeros(10, T)))
+    x = xs[0]
+    grad = Q @ x + q
+    rtol = float(np.sqrt(np.finfo(T).eps))
+    assert np.allclose(-(H * dev(grad)).numpy(), dirs[0], rtol=rtol)
+    for i in range(1, 5):
+        x_prev, grad_prev = x, grad
+        x = xs[i]
+        grad = Q @ x + q
+        H.update(dev(x - x_prev), dev(grad - grad_prev))
+        out = H.mul(dev(-grad)).numpy()
+        assert np.linalg.norm(out - dirs[i]) <= rtol * np.linalg.norm(dirs[i])
+    assert H.currmem == 3 and H.curridx == 1
+    H.reset()
+    assert np.array_equal(H.mul(dev(x)).numpy(), x) and H.currmem == 0
+
+
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("form", ["ident_quadratic", "ident_general", "matrix_A"])
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_panoc_matches_oracle_statewise(emu, golden, T, form, adaptive):
+    """Same problem on the oracle and on the product's host logic: identical control flow (backtrack counters) and
+    iterates equal up to the rounding of the reductions, iteration by iteration."""
+    d = golden("lasso_small")
+    A, b = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T)
+    n = A.shape[1]
+    kw = {} if adaptive else {"Lf": T(np.linalg.norm(A, 2) ** 2)}
+    if form == "matrix_A":
+        it_o = po.PANOCIteration(np.zeros(n, T), f=o.SquaredDistance(b), A=A, g=o.NormL1(T(1)), **kw)
+        it_p = pa.PANOCIteration(np.zeros(n, T), f=pa.SquaredDistance(b), A=A, g=pa.NormL1(T(1)), **kw)
+    else:
+        fo, fp = o.LeastSquares(A, b), pa.LeastSquares(A, b)
+        if form == "ident_general":
+            fo.is_generalized_quadratic = False
+            fp.is_generalized_quadratic = False
+        it_o = po.PANOCIteration(np.zeros(n, T), f=fo, g=o.NormL1(T(1)), **kw)
+        it_p = pa.PANOCIteration(np.zeros(n, T), f=fp, g=pa.NormL1(T(1)), **kw)
+    steps = 25
+    tol = 1e-9 if T is np.float64 else 5e-3
+    for k, (so, sp) in enumerate(zip(it_o, it_p)):
+        assert float(sp.gamma) == pytest.approx(float(so.gamma), rel=1e-6)
+        assert np.max(np.abs(sp.z.numpy() - so.z)) <= tol * max(1.0, np.max(np.abs(so.z))), (k, form)
+        assert np.max(np.abs(sp.x.numpy() - so.x)) <= tol * max(1.0, np.max(np.abs(so.x)))
+        assert np.max(np.abs(sp.res.numpy() - so.res)) <= tol
+        assert float(sp.tau) == float(so.tau), k
+        if k == steps:
+            break
+    assert it_p.tau_backtracks == it_o.tau_backtracks and it_p.backtracks == it_o.backtracks
+    assert it_o.tau_backtracks > 0                      # the line search was exercised
+    y = sp.y.numpy()
+    assert np.allclose(y, sp.x.numpy() - sp.gamma * sp.At_grad_f_Ax.numpy(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_panoc_reference_bounds(emu, golden, T):
+    # test/problems/test_lasso_small.jl:159-181 on the product's host logic
+    A, b, lam, xstar = _lasso_4x5(golden, T)
+    Lf = T(np.linalg.norm(A, 2) ** 2)
+    x0 = np.zeros(5, T)
+    x, it = pa.PANOC(tol=T(1e-4))(x0=x0, f=pa.SquaredDistance(b), A=A, g=pa.NormL1(lam), Lf=Lf)
+    assert x.dtype == T and np.max(np.abs(x - xstar)) <= 1e-4 and it < 20 and not x0.any()
+    x, it = pa.PANOC(adaptive=True, tol=T(1e-4))(x0=x0, f=pa.SquaredDistance(b), A=A, g=pa.NormL1(lam))
+    assert np.max(np.abs(x - xstar)) <= 1e-4 and it < 20
+    # FB/PANOC equivalence (test_equivalence.jl:51-83)
+    gamma = T(T(0.95) / Lf)
+    f = pa.LeastSquares(A, b)
+    f.is_generalized_quadratic = False
+    fb = iter(pa.ForwardBackwardIteration(x0, f=f, g=pa.NormL1(lam), gamma=gamma))
+    pn = iter(pa.PANOCIteration(x0, f=f, g=pa.NormL1(lam), gamma=gamma, max_backtracks=1, directions=pa.NoAcceleration()))
+    for _ in range(10):
+        s1, s2 = next(fb), next(pn)
+        assert np.allclose(s1.z.numpy(), s2.z.numpy(), rtol=float(np.sqrt(np.finfo(T).eps)), atol=0)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_panoc_user_callbacks_and_box(emu, T):
+    # test_nonconvex_qp.jl:9-36 with a user-defined smooth term (value_and_gradient on tensors) and IndBox
+    Q, q = np.diag([-0.5, 1.0]).astype(T), np.array([0.3, 0.5], T)
+
+    class Quad:
+        def value_and_gradient(self, x):
+            xv = x.numpy()
+            g = Q @ xv + q
+            return T(0.5 * xv @ (Q @ xv) + q @ xv), torch.as_tensor(g.astype(T))
+
+    x, it = pa.PANOC(tol=1e-4)(x0=np.zeros(2, T), f=Quad(), g=pa.IndBox(-1.0, 1.0))
+    gamma = 0.95
+    z = np.minimum(1.0, np.maximum(-1.0, x - gamma * (Q @ x + q)))
+    assert np.max(np.abs(x - z)) / gamma <= 1e-4
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_douglas_rachford_fused_and_unfused_match_oracle(emu, T):
+    rng = np.random.default_rng(11)
+    n = 257
+    b = rng.standard_normal(n).astype(T)
+    x0 = rng.standard_normal(n).astype(T)
+    gamma = T(0.7)
+    it_o = po.DouglasRachfordIteration(x0, f=po.SqrNormL2Translated(b, 1.5), g=o.NormL1(T(0.3)), gamma=gamma)
+    it_p = pa.DouglasRachfordIteration(x0, f=pa.SqrNormL2(1.5, b), g=pa.NormL1(0.3), gamma=gamma)
+
+    class UserL1:                                   # same g through the user `prox_` protocol -> unfused sequence
+        def prox_(self, z, y, gam):
+            zz, v = o.NormL1(T(0.3)).prox(y.numpy(), gam)
+            z.copy_(torch.as_tensor(zz))
+            return v
+
+    it_u = pa.DouglasRachfordIteration(x0, f=pa.SqrNormL2(1.5, b), g=UserL1(), gamma=gamma)
+    for k, (so, sp, su) in enumerate(zip(it_o, it_p, it_u)):
+        for name in ("x", "y", "r", "z", "res"):
+            assert np.array_equal(getattr(sp, name).numpy(), getattr(so, name)), (k, name)
+            assert np.array_equal(getattr(su, name).numpy(), getattr(so, name)), (k, name)
+        assert float(sp.res_norm_inf) == float(np.max(np.abs(so.res)))
+        if k == 12:
+            break
+    y_o, k_o = po.douglas_rachford(x0, f=po.SqrNormL2Translated(b, 1.5), g=o.NormL1(T(0.3)), gamma=gamma, tol=T(1e-5))
+    y_p, k_p = pa.DouglasRachford(tol=T(1e-5))(x0=x0, f=pa.SqrNormL2(1.5, b), g=pa.NormL1(0.3), gamma=gamma)
+    assert k_p == k_o and np.array_equal(y_p, y_o)
+    with pytest.raises(TypeError):
+        pa.DouglasRachfordIteration(x0)
