@@ -222,6 +222,17 @@ int pb_lbfgs_apply(pb_ctx* ctx, pb_lbfgs* op, const void* v, double scale, void*
 int pb_dr_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, double gamma, const pb_prox* f, const pb_prox* g,
                void* x_out, void* y, void* r, void* z, void* res);
 
+/* ---- K9: prox of the dense least-squares term (DouglasRachford's `f = LeastSquares(A, b)`, test_lasso_small.jl:39,205-214;
+ * benchmark/benchmarks.jl:87-93).  ProximalOperators' LeastSquaresDirect restated: q = lambda*A'b + x/gamma; tall A:
+ * y = (lambda*A'A + I/gamma)^-1 q; wide A: y = gamma*(q - lambda*A'((lambda*AA' + I/gamma)^-1 (A q))).  A (column-major m x n,
+ * lda = m) and b are borrowed device arrays that must outlive the operator; min(m, n) <= 4096.  The factorisation is redone
+ * (and the call synchronises) whenever gamma changes; otherwise apply is asynchronous and leaves AUX = ||A y - b||^2. */
+typedef struct pb_lsqprox pb_lsqprox;
+int pb_lsq_prox_create(pb_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, const void* b, double lambda,
+                       pb_lsqprox** out);
+int pb_lsq_prox_destroy(pb_lsqprox* op);
+int pb_lsq_prox_apply(pb_ctx* ctx, pb_lsqprox* op, const void* x, double gamma, void* y);
+
 /* ---- native driver loop ---------------------------------------------------------------------------------------------
  * The reference's IterativeAlgorithm loop (src/ProximalAlgorithms.jl:114-123) around ForwardBackward / FastForwardBackward
  * (forward_backward.jl:65-123, fast_forward_backward.jl:73-145) with the line search of fb_tools.jl:24-63, for the built-in

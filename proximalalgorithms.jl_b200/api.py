@@ -32,6 +32,7 @@ from .functions import (  # noqa: F401
     Zero,
 )
 from .panoc import PANOC, PANOCIteration, PANOCState  # noqa: F401
+from . import iteration_tools as IterationTools  # noqa: F401
 from .host import Context, DeviceExchangeComm, LocalComm, Scalars, TorchDistComm, shard_bounds  # noqa: F401
 from .nesterov import (  # noqa: F401
     AdaptiveNesterovSequence,

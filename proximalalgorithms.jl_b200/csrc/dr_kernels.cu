@@ -27,33 +27,32 @@ struct DrParams {
   XchgParams xchg;
 };
 
+// v0e / v1e: the element of the term's per-element vectors (BOX bounds, SQRL2 translation) when those vectors exist
 template <typename T>
-__device__ __forceinline__ T dr_prox(const DrProx& p, T v, int64_t i) {
+__device__ __forceinline__ T dr_prox(const DrProx& p, T v, T v0e, T v1e) {
   switch (p.kind) {
     case PB_PROX_L1:
       return prox_elem<T, PB_PROX_L1>(v, (T)p.a, T(0));
-    case PB_PROX_BOX: {
-      const T lo = p.v0 ? static_cast<const T*>(p.v0)[i] : (T)p.a;
-      const T hi = p.v1 ? static_cast<const T*>(p.v1)[i] : (T)p.b;
-      return prox_elem<T, PB_PROX_BOX>(v, lo, hi);
-    }
-    case PB_PROX_SQRL2: {
+    case PB_PROX_BOX:
+      return prox_elem<T, PB_PROX_BOX>(v, p.v0 ? v0e : (T)p.a, p.v1 ? v1e : (T)p.b);
+    case PB_PROX_SQRL2:
       // Translate(SqrNormL2(lambda), -b): w = v - b; w / (1 + gamma*lambda); + b   (three separately rounded operations)
-      if (p.v0) {
-        const T bb = static_cast<const T*>(p.v0)[i];
-        return add_rn(sub_rn(v, bb) / (T)p.a, bb);
-      }
+      if (p.v0) return add_rn(sub_rn(v, v0e) / (T)p.a, v0e);
       return v / (T)p.a;
-    }
     default:
       return v;
   }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, int UNROLL>
 __global__ void __launch_bounds__(PB_BLOCK) k_dr_step(DrParams p) {
   constexpr bool COMP = sizeof(T) == 8;
+  constexpr int64_t TILE = (int64_t)PB_BLOCK * VEC * UNROLL;
   const T* __restrict__ x = static_cast<const T*>(p.x);
+  const T* __restrict__ f0 = static_cast<const T*>(p.f.v0);
+  const T* __restrict__ f1 = static_cast<const T*>(p.f.v1);
+  const T* __restrict__ g0 = static_cast<const T*>(p.g.v0);
+  const T* __restrict__ g1 = static_cast<const T*>(p.g.v1);
   T* __restrict__ xo = static_cast<T*>(p.x_out);
   T* __restrict__ yo = static_cast<T*>(p.y);
   T* __restrict__ ro = static_cast<T*>(p.r);
@@ -61,10 +60,10 @@ __global__ void __launch_bounds__(PB_BLOCK) k_dr_step(DrParams p) {
   T* __restrict__ so = static_cast<T*>(p.res);
   Acc<1, 1> acc;
   acc.clear();
-  auto elem = [&](T xv, int64_t i, T& y, T& r, T& z, T& res, T& xn) {
-    y = dr_prox<T>(p.f, xv, i);                      // :58
+  auto elem = [&](T xv, T f0e, T f1e, T g0e, T g1e, T& y, T& r, T& z, T& res, T& xn) {
+    y = dr_prox<T>(p.f, xv, f0e, f1e);               // :58
     r = sub_rn(mul_rn(T(2), y), xv);                 // :59
-    z = dr_prox<T>(p.g, r, i);                       // :60
+    z = dr_prox<T>(p.g, r, g0e, g1e);                // :60
     res = sub_rn(y, z);                              // :61
     xn = sub_rn(xv, res);                            // :62
     const double rd = (double)res;
@@ -74,21 +73,49 @@ __global__ void __launch_bounds__(PB_BLOCK) k_dr_step(DrParams p) {
       acc.s[0].hi = __fma_rn(rd, rd, acc.s[0].hi);
     acc.m[0] = nanmax(acc.m[0], fabs(rd));
   };
-  const int64_t npacks = p.n / VEC;
-  for (int64_t q = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; q < npacks; q += (int64_t)gridDim.x * PB_BLOCK) {
-    const int64_t i = q * VEC;
-    Pack<T, VEC> xv = ld_pack<T, VEC, true>(x + i), y, r, z, res, xn;
+  auto do_pack = [&](int64_t i, const Pack<T, VEC>& xv, const Pack<T, VEC>& f0v) {
+    Pack<T, VEC> f1v, g0v, g1v, y, r, z, res, xn;
+    if (f1) f1v = ld_pack<T, VEC, false>(f1 + i);
+    if (g0) g0v = ld_pack<T, VEC, false>(g0 + i);
+    if (g1) g1v = ld_pack<T, VEC, false>(g1 + i);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) elem(xv.v[e], i + e, y.v[e], r.v[e], z.v[e], res.v[e], xn.v[e]);
+    for (int e = 0; e < VEC; ++e)
+      elem(xv.v[e], f0 ? f0v.v[e] : T(0), f1 ? f1v.v[e] : T(0), g0 ? g0v.v[e] : T(0), g1 ? g1v.v[e] : T(0), y.v[e], r.v[e],
+           z.v[e], res.v[e], xn.v[e]);
     st_pack<T, VEC, true>(xo + i, xn);
     if (yo) st_pack<T, VEC, true>(yo + i, y);
     if (ro) st_pack<T, VEC, true>(ro + i, r);
     if (zo) st_pack<T, VEC, true>(zo + i, z);
     if (so) st_pack<T, VEC, true>(so + i, res);
+  };
+  // same balanced schedule as k_step: full rounds of one TILE per CTA (UNROLL packs per stream in flight per thread), then
+  // the remaining tiles at pack granularity
+  const int64_t ntiles = p.n / TILE;
+  const int64_t rounds = ntiles / gridDim.x;
+  for (int64_t rd_ = 0; rd_ < rounds; ++rd_) {
+    const int64_t base = (rd_ * gridDim.x + blockIdx.x) * TILE + (int64_t)threadIdx.x * VEC;
+    Pack<T, VEC> xv[UNROLL], fv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = base + (int64_t)u * PB_BLOCK * VEC;
+      xv[u] = ld_pack<T, VEC, true>(x + i);
+      if (f0) fv[u] = ld_pack<T, VEC, true>(f0 + i);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) do_pack(base + (int64_t)u * PB_BLOCK * VEC, xv[u], fv[u]);
   }
-  for (int64_t i = npacks * VEC + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * PB_BLOCK) {
+  const int64_t rem_start = rounds * gridDim.x * TILE;
+  const int64_t rem_packs = (p.n - rem_start) / VEC;
+  for (int64_t q = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; q < rem_packs; q += (int64_t)gridDim.x * PB_BLOCK) {
+    const int64_t i = rem_start + q * VEC;
+    Pack<T, VEC> xq = ld_pack<T, VEC, true>(x + i), fq;
+    if (f0) fq = ld_pack<T, VEC, true>(f0 + i);
+    do_pack(i, xq, fq);
+  }
+  for (int64_t i = rem_start + rem_packs * VEC + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < p.n;
+       i += (int64_t)gridDim.x * PB_BLOCK) {
     T y, r, z, res, xn;
-    elem(x[i], i, y, r, z, res, xn);
+    elem(x[i], f0 ? f0[i] : T(0), f1 ? f1[i] : T(0), g0 ? g0[i] : T(0), g1 ? g1[i] : T(0), y, r, z, res, xn);
     xo[i] = xn;
     if (yo) yo[i] = y;
     if (ro) ro[i] = r;
@@ -159,16 +186,29 @@ extern "C" int pb_dr_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, doub
   const void* ptrs[] = {x, x_out, y, r, z, res, p.f.v0, p.f.v1, p.g.v0, p.g.v1};
   bool vec_ok = true;
   for (const void* q : ptrs) vec_ok = vec_ok && (!q || pb_aligned16(q));
+  // grid = SMs x co-resident CTAs (a partial second wave of a grid-stride kernel serialises, see step_kernels.cu)
+  auto launch = [&](auto kern, int64_t work_per_cta) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PB_BLOCK, 0) != cudaSuccess || occ < 1) occ = 1;
+    int per_sm = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 4;
+    if (per_sm > occ) per_sm = occ;
+    int64_t g_ = (int64_t)ctx->sm_count * per_sm;
+    const int64_t need = (n + work_per_cta - 1) / work_per_cta;
+    if (g_ > need) g_ = need;
+    if (g_ < 1) g_ = 1;
+    if (g_ > PB_MAX_CTAS) g_ = PB_MAX_CTAS;
+    kern<<<(unsigned)g_, PB_BLOCK, 0, ctx->stream>>>(p);
+  };
   if (dtype == PB_F32) {
     if (vec_ok)
-      k_dr_step<float, 4><<<pb_stream_grid(ctx, PB_BLOCK * 4 * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+      launch(k_dr_step<float, 4, 4>, (int64_t)PB_BLOCK * 4 * 4);
     else
-      k_dr_step<float, 1><<<pb_stream_grid(ctx, PB_BLOCK * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+      launch(k_dr_step<float, 1, 4>, (int64_t)PB_BLOCK * 4);
   } else {
     if (vec_ok)
-      k_dr_step<double, 2><<<pb_stream_grid(ctx, PB_BLOCK * 2 * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+      launch(k_dr_step<double, 2, 4>, (int64_t)PB_BLOCK * 2 * 4);
     else
-      k_dr_step<double, 1><<<pb_stream_grid(ctx, PB_BLOCK * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+      launch(k_dr_step<double, 1, 4>, (int64_t)PB_BLOCK * 4);
   }
   PB_LAUNCH_CHECK(ctx);
   return PB_OK;

@@ -53,6 +53,81 @@ __global__ void __launch_bounds__(GEMV_ROWS* GEMV_CL)
   }
 }
 
+// partial product for SHORT columns (mb < 64, e.g. the 4 x 128000 blocks of the group-lasso workload): the thread-per-row
+// kernel above would keep mb of its 128 row lanes busy.  Mirror image of k_gemv_t_sub: LPC lanes share one column, each lane
+// owns up to KP 16-byte packs of it and accumulates a_ij * x_j into its own row accumulators while the CTA sweeps the
+// columns of its chunk (coalesced 16-byte loads of A, 4 sweeps in flight); the column lanes are folded with a fixed
+// shuffle tree, the warps through shared memory in warp order.  One CTA = one column chunk of ONE block, so -- like the
+// kernel above -- the summation order depends on the block shape only.
+template <typename T, int LPC, int KP>
+__global__ void __launch_bounds__(PB_BLOCK) k_gemv_n_sub(const T* __restrict__ A, int64_t lda, int64_t blk_stride,
+                                                         const T* __restrict__ x, T* __restrict__ partial, int64_t mb,
+                                                         int64_t nb, int64_t nblk, int64_t chunk_cols, int64_t chunks_per_blk) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int CPW = 32 / LPC;
+  constexpr int WARPS = PB_BLOCK / 32;
+  constexpr int SW = 4;                               // column sweeps in flight
+  __shared__ T sh[WARPS][LPC * KP * VEC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPC, colw = lane / LPC;
+  const int64_t k = blockIdx.x / chunks_per_blk, chunk = blockIdx.x % chunks_per_blk;
+  const int64_t c0 = chunk * chunk_cols;
+  int64_t c1 = c0 + chunk_cols;
+  if (c1 > nb) c1 = nb;
+  const T* __restrict__ Ak = A + k * blk_stride;
+  const T* __restrict__ xk = x + k * nb;
+  const int64_t npk = mb / VEC;
+  T acc[KP][VEC];
+#pragma unroll
+  for (int q = 0; q < KP; ++q)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[q][e] = T(0);
+  const int64_t stride = (int64_t)WARPS * CPW;
+  for (int64_t j0 = c0 + (int64_t)warp * CPW + colw; j0 < c1; j0 += SW * stride) {
+    Pack<T, VEC> av[SW][KP];
+    T xv[SW];
+#pragma unroll
+    for (int s_ = 0; s_ < SW; ++s_) {
+      const int64_t j = j0 + s_ * stride;
+      const bool live = j < c1;
+      xv[s_] = live ? __ldg(xk + j) : T(0);
+      const T* __restrict__ a = Ak + (live ? j : c0) * lda;
+#pragma unroll
+      for (int q = 0; q < KP; ++q) {
+        const int64_t pk = sub + (int64_t)q * LPC;
+        if (pk < npk) av[s_][q] = ld_pack<T, VEC, true>(a + pk * VEC);
+      }
+    }
+#pragma unroll
+    for (int s_ = 0; s_ < SW; ++s_)
+#pragma unroll
+      for (int q = 0; q < KP; ++q) {
+        const int64_t pk = sub + (int64_t)q * LPC;
+        if (pk < npk) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[q][e] = fma(av[s_][q].v[e], xv[s_], acc[q][e]);
+        }
+      }
+  }
+  // fold the column lanes of the warp (lanes with equal `sub`), then the warps in order
+#pragma unroll
+  for (int q = 0; q < KP; ++q)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      T v = acc[q][e];
+#pragma unroll
+      for (int off = 16; off >= LPC; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (colw == 0) sh[warp][(q * LPC + sub) * VEC + e] = v;
+    }
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < mb; i += PB_BLOCK) {
+    T s_ = sh[0][i];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) s_ += sh[w][i];
+    partial[(chunk * nblk + k) * mb + i] = s_;
+  }
+}
+
 // r[i] = (sum_chunks partial[c][i]) - b[i];  AUX = sum r^2
 template <typename T>
 __global__ void __launch_bounds__(PB_BLOCK) k_gemv_n_combine(const T* __restrict__ partial, int nchunk, int64_t M,
@@ -189,9 +264,29 @@ static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
   int rc = pb_ensure_scratch(ctx, (size_t)nchunk * M * sizeof(T));
   if (rc != PB_OK) return rc;
   T* partial = static_cast<T*>(ctx->scratch);
-  dim3 grid((unsigned)row_tiles, (unsigned)nchunk, (unsigned)nblk);
-  k_gemv_n_partial<T><<<grid, GEMV_ROWS * GEMV_CL, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk,
-                                                                    chunk_cols);
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int KP = 4;
+  const int64_t npk = mb / VEC;
+  const bool sub_ok = mb < 64 && mb % VEC == 0 && lda % VEC == 0 && blk_stride % VEC == 0 && pb_aligned16(A) &&
+                      nblk * nchunk <= 0x7fffffffLL;
+  if (sub_ok) {
+    int lpc = 1;
+    while ((int64_t)lpc * KP < npk) lpc <<= 1;
+#define PB_LAUNCH_NSUB(L)                                                                                              \
+  k_gemv_n_sub<T, L, KP><<<(unsigned)(nblk * nchunk), PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk, \
+                                                                                 chunk_cols, nchunk)
+    switch (lpc) {
+      case 1: PB_LAUNCH_NSUB(1); break;
+      case 2: PB_LAUNCH_NSUB(2); break;
+      case 4: PB_LAUNCH_NSUB(4); break;
+      default: PB_LAUNCH_NSUB(8); break;
+    }
+#undef PB_LAUNCH_NSUB
+  } else {
+    dim3 grid((unsigned)row_tiles, (unsigned)nchunk, (unsigned)nblk);
+    k_gemv_n_partial<T><<<grid, GEMV_ROWS * GEMV_CL, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk,
+                                                                      chunk_cols);
+  }
   PB_LAUNCH_CHECK(ctx);
   const int cgrid = pb_stream_grid(ctx, PB_BLOCK, M, 2);
   k_gemv_n_combine<T><<<cgrid, PB_BLOCK, 0, ctx->stream>>>(partial, (int)nchunk, M, b, r, ctx->ws, ctx->scalars_dev);

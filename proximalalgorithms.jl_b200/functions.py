@@ -165,6 +165,30 @@ class LeastSquares:
         self.calls += 1
         return self._residual(x)
 
+    # ---- as a PROXIMABLE term (DouglasRachford's f, test/problems/test_lasso_small.jl:39,205-214) ---------------------
+    def prox_enqueue(self, ctx, y, x, gamma, comm=None):
+        """prox!(y, f, x, gamma) of ProximalOperators' LeastSquaresDirect (K9, csrc/lsq_prox.cu); AUX = ||A y - b||^2."""
+        if self.comm.size != 1:
+            raise L.ProxB200Error("the factorised least-squares prox is single-GPU")
+        if getattr(self, "_prox_h", None) is None:
+            h = C.c_void_p()
+            L.check(ctx.lib.pb_lsq_prox_create(ctx.h, pb_dtype(self.R), self.m, self.n, ptr(self.A_cm), ptr(self.b), 1.0, C.byref(h)))
+            self._prox_h = h
+        L.check(ctx.lib.pb_lsq_prox_apply(ctx.h, self._prox_h, ptr(x), float(self.R(gamma)), ptr(y)))
+
+    def prox_(self, y, x, gamma):
+        self.prox_enqueue(self.ctx, y, x, gamma)
+        row = self.ctx.read_scalars()
+        return _sq_half(self.R, row[L.PB_S_AUX] + row[L.PB_S_AUX + 1])
+
+    def __del__(self):
+        h, self._prox_h = getattr(self, "_prox_h", None), None
+        if h is not None:
+            try:
+                self.ctx.lib.pb_lsq_prox_destroy(h)
+            except Exception:
+                pass
+
     def native_descriptor(self):
         """pb_smooth for the native driver (single GPU only: column shards need a vector all-gather per evaluation)."""
         if self.comm.size != 1:

@@ -340,6 +340,31 @@ class EmuLib:
             _vec(x_d, n, dt)[...] = (_vec(x, n, dt) + dv).astype(T)
         return 0
 
+    # ---- K9: least-squares prox ---------------------------------------------------------------------------------------
+    def pb_lsq_prox_create(self, h, dt, m, n, A, b, lam, out):
+        key = self._next
+        self._next += 1
+        Am = _vec(A, m * n, dt).reshape(n, m).T.astype(np.float64)
+        self._lb[key] = ("lsqprox", dt, m, n, Am, _vec(b, m, dt).astype(np.float64), lam)
+        out._obj.value = key
+        return 0
+
+    def pb_lsq_prox_destroy(self, op):
+        self._lb.pop(_addr(op), None)
+        return 0
+
+    def pb_lsq_prox_apply(self, h, op, x, gamma, y):
+        _, dt, m, n, Am, b, lam = self._lb[_addr(op)]
+        T = np.float32 if dt == L.PB_F32 else np.float64
+        self.launches += 4
+        gamma = float(T(gamma))
+        xv = _vec(x, n, dt).astype(np.float64)
+        yv = np.linalg.solve(lam * Am.T @ Am + np.eye(n) / gamma, lam * Am.T @ b + xv / gamma).astype(T)
+        _vec(y, n, dt)[...] = yv
+        r = (Am @ yv.astype(np.float64) - b).astype(T)
+        self._set(L.PB_S_AUX, _fsum_prod(r, r))
+        return 0
+
     # ---- K8: Douglas-Rachford ----------------------------------------------------------------------------------------
     def pb_dr_step(self, h, dt, n, x, gamma, f, g, x_out, y, r, z, res):
         T = np.float32 if dt == L.PB_F32 else np.float64

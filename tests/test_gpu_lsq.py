@@ -24,7 +24,8 @@ def _tol(T, k):
 
 
 @pytest.mark.parametrize("T", TYPES)
-@pytest.mark.parametrize("m,n", [(4, 5), (5, 10), (50, 100), (500, 1000), (200, 500), (1, 1), (129, 3), (3, 700), (1000, 33)])
+@pytest.mark.parametrize("m,n", [(4, 5), (5, 10), (50, 100), (500, 1000), (200, 500), (1, 1), (129, 3), (3, 700), (1000, 33),
+                                 (4, 100_000), (16, 5000), (48, 2500)])
 def test_dense_value_and_gradient(T, m, n):
     rng = np.random.default_rng(m * 1000 + n)
     A = np.asfortranarray(rng.standard_normal((m, n)).astype(T))
@@ -62,7 +63,9 @@ def test_dense_value_matches_oracle_on_fixtures():
 
 
 @pytest.mark.parametrize("T", TYPES)
-@pytest.mark.parametrize("nblk,mb,nb", [(1, 4, 5), (7, 100, 1000), (3, 33, 77), (100, 10, 257), (2, 200, 4096)])
+@pytest.mark.parametrize("nblk,mb,nb", [(1, 4, 5), (7, 100, 1000), (3, 33, 77), (100, 10, 257), (2, 200, 4096),
+                                        # short columns -> k_gemv_n_sub (1, 2, 4, 8 lanes per column), ragged chunks
+                                        (5, 4, 3001), (3, 8, 12800), (9, 16, 700), (4, 32, 1023), (2, 60, 333), (3, 62, 4100), (1, 2, 9)])
 def test_blockdiag_value_and_gradient(T, nblk, mb, nb):
     rng = np.random.default_rng(nblk + mb + nb)
     blocks = rng.standard_normal((nblk, mb, nb)).astype(T)

@@ -178,3 +178,15 @@ def test_douglas_rachford_fused_and_unfused_match_oracle(emu, T):
     assert k_p == k_o and np.array_equal(y_p, y_o)
     with pytest.raises(TypeError):
         pa.DouglasRachfordIteration(x0)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_douglas_rachford_least_squares_like_the_reference(emu, golden, T):
+    # test/problems/test_lasso_small.jl:205-214 through the unfused sequence with the factorised least-squares prox
+    A, b, lam, xstar = _lasso_4x5(golden, T)
+    gamma = T(T(10) / T(np.linalg.norm(A, 2) ** 2))
+    x0 = np.zeros(5, T)
+    y, it = pa.DouglasRachford(tol=T(1e-4))(x0=x0, f=pa.LeastSquares(A, b), g=pa.NormL1(lam), gamma=gamma)
+    y_o, it_o = po.douglas_rachford(x0, f=po.LeastSquaresProx(A, b), g=o.NormL1(lam), gamma=gamma, tol=T(1e-4))
+    assert y.dtype == T and np.max(np.abs(y - xstar)) <= 1e-4 and it < 30 and not x0.any()
+    assert abs(it - it_o) <= 1 and np.max(np.abs(y - y_o)) <= (1e-9 if T is np.float64 else 1e-4)
