@@ -216,11 +216,28 @@ int pb_lbfgs_apply(pb_ctx* ctx, pb_lbfgs* op, const void* v, double scale, void*
 
 /* ---- K8: fused Douglas-Rachford iteration (src/algorithms/douglas_rachford.jl:54-63) -----------------------------
  * y = prox_{gamma f}(x); r = 2y - x; z = prox_{gamma g}(r); res = y - z; x_out = x - res in ONE pass, with RESINF =
- * norm(res, Inf) (stop rule, :65-69) and RESSQ = ||res||^2.  f and g must be element-wise kinds (ZERO, L1, BOX, SQRL2);
+ * norm(res, Inf) (stop rule, :65-69).  f and g must be element-wise kinds (ZERO, L1, BOX, SQRL2);
  * PB_EUNSUPPORTED otherwise.  x_out may alias x.  y, r, z, res are optional outputs (NULL = not materialised).
  * Algorithmic traffic: 2 vectors (read x, write x_out), +1 for the data vector of SQRL2. */
 int pb_dr_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, double gamma, const pb_prox* f, const pb_prox* g,
                void* x_out, void* y, void* r, void* z, void* res);
+
+/* ---- K10: Douglas-Rachford iteration of anisotropic TV denoising in consensus form (BASELINE.json configs[4]) -------
+ * minimize 0.5*||u - b||^2 + lambda*TV(u) split into five terms (data, even/odd horizontal pairs, even/odd vertical
+ * pairs) on five stacked copies x[5][H][W] (row-major images); one call = one whole iteration of
+ * douglas_rachford.jl:54-63 with F = separable sum of the five proxes and G = consensus (average), in ONE pass:
+ * reads x (and b), writes x_out (must not alias x), RESINF = max|res| over the five copies; y[5][H][W] and the consensus
+ * image z[H][W] are optional outputs.  TV is not in the reference: the splitting is ours (csrc/tv_kernels.cu,
+ * oracle/tv_oracle.py; parity unpinned).  Row shards: this call owns global rows [row0, row0 + H) of an Hglob-row image;
+ * halo_prev / halo_next point to the ONE neighbouring row (of the copy whose vertical pair straddles the shard boundary)
+ * inside the neighbour's x buffer, typically peer memory opened with pb_ipc_open (read over NVLink), NULL at the border. */
+int pb_dr_tv_step(pb_ctx* ctx, int dtype, int64_t H, int64_t W, const void* x, const void* b, double gamma, double lambda,
+                  void* x_out, void* y, void* z, int64_t row0, int64_t Hglob, const void* halo_prev,
+                  const void* halo_next);
+/* cudaIpc plumbing for buffers other ranks read directly (pb_malloc'ed memory only; handles are PB_IPC_HANDLE_BYTES). */
+int pb_ipc_export(pb_ctx* ctx, void* dptr, void* handle_out);
+int pb_ipc_open(pb_ctx* ctx, const void* handle, void** dptr);
+int pb_ipc_close(pb_ctx* ctx, void* dptr);
 
 /* ---- K9: prox of the dense least-squares term (DouglasRachford's `f = LeastSquares(A, b)`, test_lasso_small.jl:39,205-214;
  * benchmark/benchmarks.jl:87-93).  ProximalOperators' LeastSquaresDirect restated: q = lambda*A'b + x/gamma; tall A:

@@ -110,6 +110,10 @@ SIGNATURES = {
     "pb_lbfgs_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pb_lbfgs_commit": (_i, [_vp, _d, _d, C.POINTER(C.c_int)]),
     "pb_lbfgs_apply": (_i, [_vp, _vp, _vp, _d, _vp, _vp, _vp]),
+    "pb_dr_tv_step": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _d, _d, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "pb_ipc_export": (_i, [_vp, _vp, _vp]),
+    "pb_ipc_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "pb_ipc_close": (_i, [_vp, _vp]),
     "pb_lsq_prox_create": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _d, C.POINTER(_vp)]),
     "pb_lsq_prox_destroy": (_i, [_vp]),
     "pb_lsq_prox_apply": (_i, [_vp, _vp, _vp, _d, _vp]),

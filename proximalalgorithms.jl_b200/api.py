@@ -31,6 +31,7 @@ from .functions import (  # noqa: F401
     SquaredDistance,
     Zero,
 )
+from .tv import IndConsensus, TVSplit  # noqa: F401
 from .panoc import PANOC, PANOCIteration, PANOCState  # noqa: F401
 from . import iteration_tools as IterationTools  # noqa: F401
 from .host import Context, DeviceExchangeComm, LocalComm, Scalars, TorchDistComm, shard_bounds  # noqa: F401

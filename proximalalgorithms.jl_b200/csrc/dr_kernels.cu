@@ -5,7 +5,7 @@
 // The reference makes five passes over six vectors (prox!, broadcast, prox!, broadcast, broadcast, norm: 13 vector
 // reads/writes per element).  Here the whole iteration is ONE pass: read x (+ the data vector b of a translated
 // quadratic), write x; y, r, z, res are only materialised on request (lazy state fields / the final solution), and
-// norm(res, Inf), ||res||^2 come out of the same pass.  Algorithmic traffic: 2 vectors per iteration (3 with b).
+// norm(res, Inf) comes out of the same pass.  Algorithmic traffic: 2 vectors per iteration (3 with b).
 // HBM-bound streaming kernel, no tensor-core formulation exists.
 #include "step_common.cuh"
 
@@ -28,9 +28,11 @@ struct DrParams {
 };
 
 // v0e / v1e: the element of the term's per-element vectors (BOX bounds, SQRL2 translation) when those vectors exist
-template <typename T>
+// K >= 0: the kind is a compile-time constant (no per-element dispatch); K < 0: read it from the descriptor
+template <typename T, int K>
 __device__ __forceinline__ T dr_prox(const DrProx& p, T v, T v0e, T v1e) {
-  switch (p.kind) {
+  const int kind = K >= 0 ? K : p.kind;
+  switch (kind) {
     case PB_PROX_L1:
       return prox_elem<T, PB_PROX_L1>(v, (T)p.a, T(0));
     case PB_PROX_BOX:
@@ -44,9 +46,8 @@ __device__ __forceinline__ T dr_prox(const DrProx& p, T v, T v0e, T v1e) {
   }
 }
 
-template <typename T, int VEC, int UNROLL>
+template <typename T, int VEC, int UNROLL, int FK, int GK>
 __global__ void __launch_bounds__(PB_BLOCK) k_dr_step(DrParams p) {
-  constexpr bool COMP = sizeof(T) == 8;
   constexpr int64_t TILE = (int64_t)PB_BLOCK * VEC * UNROLL;
   const T* __restrict__ x = static_cast<const T*>(p.x);
   const T* __restrict__ f0 = static_cast<const T*>(p.f.v0);
@@ -58,20 +59,17 @@ __global__ void __launch_bounds__(PB_BLOCK) k_dr_step(DrParams p) {
   T* __restrict__ ro = static_cast<T*>(p.r);
   T* __restrict__ zo = static_cast<T*>(p.z);
   T* __restrict__ so = static_cast<T*>(p.res);
-  Acc<1, 1> acc;
-  acc.clear();
+  // The only reduction is the stop norm max|res| (NaN-propagating), kept in the element type: the pass moves 8-12 bytes per
+  // element, so per-element conversions to double (ncu: XU / ADU pipes) would make it instruction-bound.
+  T mx = T(0);
   auto elem = [&](T xv, T f0e, T f1e, T g0e, T g1e, T& y, T& r, T& z, T& res, T& xn) {
-    y = dr_prox<T>(p.f, xv, f0e, f1e);               // :58
+    y = dr_prox<T, FK>(p.f, xv, f0e, f1e);           // :58
     r = sub_rn(mul_rn(T(2), y), xv);                 // :59
-    z = dr_prox<T>(p.g, r, g0e, g1e);                // :60
+    z = dr_prox<T, GK>(p.g, r, g0e, g1e);            // :60
     res = sub_rn(y, z);                              // :61
     xn = sub_rn(xv, res);                            // :62
-    const double rd = (double)res;
-    if (COMP)
-      dd_add_prod(acc.s[0], rd, rd);
-    else
-      acc.s[0].hi = __fma_rn(rd, rd, acc.s[0].hi);
-    acc.m[0] = nanmax(acc.m[0], fabs(rd));
+    const T ar = fabs(res);
+    mx = (ar > mx || ar != ar) ? ar : mx;
   };
   auto do_pack = [&](int64_t i, const Pack<T, VEC>& xv, const Pack<T, VEC>& f0v) {
     Pack<T, VEC> f1v, g0v, g1v, y, r, z, res, xn;
@@ -122,12 +120,14 @@ __global__ void __launch_bounds__(PB_BLOCK) k_dr_step(DrParams p) {
     if (zo) zo[i] = z;
     if (so) so[i] = res;
   }
+  Acc<0, 1> acc;
+  acc.clear();
+  acc.m[0] = (double)mx;
   OutMap map;
-  map.sum_slot[0] = PB_S_RESSQ;
-  map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
+  map.sum_slot[0] = map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
   map.max_slot[0] = PB_S_RESINF;
   map.max_slot[1] = -1;
-  grid_reduce<1, 1, PB_BLOCK>(acc, p.ws, p.outs, map, &p.xchg);
+  grid_reduce<0, 1, PB_BLOCK>(acc, p.ws, p.outs, map, &p.xchg);
 }
 
 // prox parameters in the element type, combined on the host with one rounding each (like the package does)
@@ -190,7 +190,7 @@ extern "C" int pb_dr_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, doub
   auto launch = [&](auto kern, int64_t work_per_cta) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PB_BLOCK, 0) != cudaSuccess || occ < 1) occ = 1;
-    int per_sm = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 4;
+    int per_sm = ctx->ctas_per_sm > 0 ? ctx->ctas_per_sm : 8;
     if (per_sm > occ) per_sm = occ;
     int64_t g_ = (int64_t)ctx->sm_count * per_sm;
     const int64_t need = (n + work_per_cta - 1) / work_per_cta;
@@ -199,17 +199,51 @@ extern "C" int pb_dr_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, doub
     if (g_ > PB_MAX_CTAS) g_ = PB_MAX_CTAS;
     kern<<<(unsigned)g_, PB_BLOCK, 0, ctx->stream>>>(p);
   };
+  // packs in flight per thread and stream: PB_OPT_UNROLL (1, 2, 4); default from the sweep in profiles/r01_next_rows.md.
+  // The prox kinds are compile-time parameters of the vectorised kernels (16 pairs); misaligned views take a generic kernel.
+  const int unroll = ctx->unroll == 1 || ctx->unroll == 2 || ctx->unroll == 4 ? ctx->unroll : 2;
+  const int fk = p.f.kind, gk = p.g.kind;
+#define PB_DR_U(T, VEC, FK, GK)                                                                  \
+  do {                                                                                           \
+    if (unroll == 4)                                                                             \
+      launch(k_dr_step<T, VEC, 4, FK, GK>, (int64_t)PB_BLOCK * VEC * 4);                         \
+    else if (unroll == 2)                                                                        \
+      launch(k_dr_step<T, VEC, 2, FK, GK>, (int64_t)PB_BLOCK * VEC * 2);                         \
+    else                                                                                         \
+      launch(k_dr_step<T, VEC, 1, FK, GK>, (int64_t)PB_BLOCK * VEC);                             \
+  } while (0)
+#define PB_DR_G(T, VEC, FK)                                                                      \
+  do {                                                                                           \
+    switch (gk) {                                                                                \
+      case PB_PROX_ZERO: PB_DR_U(T, VEC, FK, PB_PROX_ZERO); break;                               \
+      case PB_PROX_L1: PB_DR_U(T, VEC, FK, PB_PROX_L1); break;                                   \
+      case PB_PROX_BOX: PB_DR_U(T, VEC, FK, PB_PROX_BOX); break;                                 \
+      default: PB_DR_U(T, VEC, FK, PB_PROX_SQRL2); break;                                        \
+    }                                                                                            \
+  } while (0)
+#define PB_DR_F(T, VEC)                                                                          \
+  do {                                                                                           \
+    switch (fk) {                                                                                \
+      case PB_PROX_ZERO: PB_DR_G(T, VEC, PB_PROX_ZERO); break;                                   \
+      case PB_PROX_L1: PB_DR_G(T, VEC, PB_PROX_L1); break;                                       \
+      case PB_PROX_BOX: PB_DR_G(T, VEC, PB_PROX_BOX); break;                                     \
+      default: PB_DR_G(T, VEC, PB_PROX_SQRL2); break;                                            \
+    }                                                                                            \
+  } while (0)
   if (dtype == PB_F32) {
     if (vec_ok)
-      launch(k_dr_step<float, 4, 4>, (int64_t)PB_BLOCK * 4 * 4);
+      PB_DR_F(float, 4);
     else
-      launch(k_dr_step<float, 1, 4>, (int64_t)PB_BLOCK * 4);
+      launch(k_dr_step<float, 1, 4, -1, -1>, (int64_t)PB_BLOCK * 4);
   } else {
     if (vec_ok)
-      launch(k_dr_step<double, 2, 4>, (int64_t)PB_BLOCK * 2 * 4);
+      PB_DR_F(double, 2);
     else
-      launch(k_dr_step<double, 1, 4>, (int64_t)PB_BLOCK * 4);
+      launch(k_dr_step<double, 1, 4, -1, -1>, (int64_t)PB_BLOCK * 4);
   }
+#undef PB_DR_F
+#undef PB_DR_G
+#undef PB_DR_U
   PB_LAUNCH_CHECK(ctx);
   return PB_OK;
 }

@@ -19,6 +19,7 @@ from . import _lib as L
 from .algorithms import IterativeAlgorithm, _Engine, _to_device_copy
 from .functions import Zero
 from .host import pb_dtype, ptr, real_type, torch
+from .tv import IndConsensus, TVDouglasRachfordEngine
 
 _ELEMENTWISE = (L.PB_PROX_ZERO, L.PB_PROX_L1, L.PB_PROX_BOX, L.PB_PROX_SQRL2)
 
@@ -35,6 +36,8 @@ class DouglasRachfordState:
         self._mat_valid = False
 
     def _materialise(self):
+        if self._tv is not None:
+            return self._materialise_tv()
         if self._fused and not self._mat_valid:
             t = torch()
             if self._mat is None:
@@ -47,10 +50,38 @@ class DouglasRachfordState:
             self._mat_valid = True
         return self._mat
 
-    y = property(lambda self: self._materialise()[0] if self._fused else self._y)
-    r = property(lambda self: self._materialise()[1] if self._fused else self._r)
-    z = property(lambda self: self._materialise()[2] if self._fused else self._z)
-    res = property(lambda self: self._materialise()[3] if self._fused else self._res)
+    def _materialise_tv(self):
+        """TV consensus form: y (five stacked copies) and the consensus image z are written by re-running the last pass.
+        Row-sharded runs: a COLLECTIVE operation (every rank must ask at the same iteration), fenced by two barriers so that
+        no neighbour overwrites the buffer the halo rows are read from."""
+        if not self._mat_valid:
+            t = torch()
+            eng, it = self._tv, self._it
+            if self._mat is None:
+                n = it.f.H * it.f.W
+                self._mat = (t.empty(5 * n, dtype=self.x.dtype, device=self.x.device), None,
+                             t.empty(n, dtype=self.x.dtype, device=self.x.device), None)
+            if eng.sharded:
+                it.f.comm.dist.barrier(group=getattr(it.f.comm, "group", None))
+            eng.step(it.gamma, y=self._mat[0], z=self._mat[2], redo=True)
+            if eng.sharded:
+                t.cuda.synchronize(self.x.device)
+                it.f.comm.dist.barrier(group=getattr(it.f.comm, "group", None))
+            self._mat_valid = True
+        return self._mat
+
+    def _field(self, k, name):
+        if self._fused or self._tv is not None:
+            v = self._materialise()[k]
+            if v is None:
+                raise AttributeError(f"state.{name} is not materialised by the fused TV iteration (y and z are)")
+            return v
+        return getattr(self, "_" + name)
+
+    y = property(lambda self: self._field(0, "y"))
+    r = property(lambda self: self._field(1, "r"))
+    z = property(lambda self: self._field(2, "z"))
+    res = property(lambda self: self._field(3, "res"))
 
     @property
     def res_norm_inf(self):
@@ -68,6 +99,8 @@ class DouglasRachfordIteration:
         self.f = f if f is not None else Zero()
         self.g = g if g is not None else Zero()
         self.gamma = self.R(gamma)
+        if comm is None and getattr(self.f, "tv_split", False) and self.f.comm.size > 1:
+            comm = self.f.comm                        # the row-sharded TV term carries the communicator of the run
         self.comm = comm
 
     def _prox(self, e, term, out, inp):
@@ -85,15 +118,27 @@ class DouglasRachfordIteration:
             e = _Engine(self, self.x0)
             st._engine, st._R, st._it = e, R, self
             st.x = _to_device_copy(self.x0, e.ctx)                                          # :56
-            st._fused = _elementwise(self.f) and _elementwise(self.g)
-            if st._fused:
+            st._tv = None
+            if getattr(self.f, "tv_split", False) and isinstance(self.g, IndConsensus):
+                if self.g.K != self.f.ncopies:
+                    raise ValueError("IndConsensus(K) must match the five copies of TVSplit")
+                st._tv = TVDouglasRachfordEngine(self.f, st.x)
+                st._fused = False
+            else:
+                st._fused = _elementwise(self.f) and _elementwise(self.g)
+            if st._tv is not None:
+                pass
+            elif st._fused:
                 self._fd, self._gd = self.f.descriptor(R), self.g.descriptor(R)
                 st._x_in = t.empty_like(st.x)
             else:
                 st._y, st._r, st._z, st._res = (t.empty_like(st.x) for _ in range(4))
         e = st._engine
         dt, n = pb_dtype(R), st.x.numel()
-        if st._fused:
+        if st._tv is not None:
+            st.x = st._tv.step(self.gamma)                                                  # :58-62 in one pass (K10)
+            st._mat_valid = False
+        elif st._fused:
             st._x_in, st.x = st.x, st._x_in
             L.check(e.lib.pb_dr_step(e.ctx.h, dt, n, ptr(st._x_in), float(self.gamma), C.byref(self._fd), C.byref(self._gd),
                                      ptr(st.x), None, None, None, None))

@@ -382,9 +382,33 @@ class EmuLib:
         for p, val in ((y, yv), (r, rv), (z, zv), (res, sv)):
             if _addr(p):
                 _vec(p, n, dt)[...] = val
-        self._set(L.PB_S_RESSQ, _fsum_prod(sv, sv))
         self.scal[L.PB_S_RESINF] = float(np.max(np.abs(sv))) if n else 0.0
         return 0
+
+
+def _tv_step(self, h, dt, H, W, x, b, gamma, lam, x_out, y, z, row0, Hglob, hp, hn):
+    """pb_dr_tv_step through the numpy oracle of the splitting (single shard: no halos on the CPU emulation)."""
+    from oracle import tv_oracle as tvo
+
+    T = np.float32 if dt == L.PB_F32 else np.float64
+    self.launches += 1
+    n = H * W
+    xv = _vec(x, 5 * n, dt).copy()
+    f = tvo.TVSplit(_vec(b, n, dt).copy(), T(lam), (H, W), row0, Hglob)
+    yv, _ = f.prox(xv, T(gamma))
+    rv = (T(2) * yv - xv).astype(T)
+    zt, _ = tvo.Consensus(5).prox(rv, T(gamma))
+    res = (yv - zt).astype(T)
+    _vec(x_out, 5 * n, dt)[...] = (xv - res).astype(T)
+    if _addr(y):
+        _vec(y, 5 * n, dt)[...] = yv
+    if _addr(z):
+        _vec(z, n, dt)[...] = zt[:n]
+    self.scal[L.PB_S_RESINF] = float(np.max(np.abs(res))) if n else 0.0
+    return 0
+
+
+EmuLib.pb_dr_tv_step = _tv_step
 
 
 class EmuContext:

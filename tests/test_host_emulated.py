@@ -9,6 +9,7 @@ import torch
 import proxb200 as pa
 from oracle import fb_oracle as o
 from oracle import panoc_oracle as po
+from oracle import tv_oracle as tvo
 from proxb200 import algorithms, functions, host
 
 from emu_lib import EmuContext
@@ -190,3 +191,25 @@ def test_douglas_rachford_least_squares_like_the_reference(emu, golden, T):
     y_o, it_o = po.douglas_rachford(x0, f=po.LeastSquaresProx(A, b), g=o.NormL1(lam), gamma=gamma, tol=T(1e-4))
     assert y.dtype == T and np.max(np.abs(y - xstar)) <= 1e-4 and it < 30 and not x0.any()
     assert abs(it - it_o) <= 1 and np.max(np.abs(y - y_o)) <= (1e-9 if T is np.float64 else 1e-4)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_tv_douglas_rachford_host_logic(emu, T):
+    rng = np.random.default_rng(3)
+    H, W = 10, 12
+    b = (np.kron(rng.standard_normal((2, 3)), np.ones((5, 4))) + 0.1 * rng.standard_normal((H, W))).astype(T)
+    lam, gamma = 0.25, T(1.0)
+    f = pa.TVSplit(b, lam)
+    x0 = f.initial_point()
+    it_p = iter(pa.DouglasRachfordIteration(x0, f=f, g=pa.IndConsensus(5), gamma=gamma))
+    it_o = iter(po.DouglasRachfordIteration(np.tile(b.reshape(-1), 5), f=tvo.TVSplit(b, T(lam), (H, W)), g=tvo.Consensus(5), gamma=gamma))
+    for k in range(8):
+        sp, so = next(it_p), next(it_o)
+        assert np.array_equal(sp.x.numpy(), so.x) and np.array_equal(sp.y.numpy(), so.y)
+        assert np.array_equal(sp.z.numpy(), so.z[: H * W])
+        assert float(sp.res_norm_inf) == float(np.max(np.abs(so.res)))
+    y, k = pa.DouglasRachford(tol=T(1e-4), maxit=3000)(x0=x0, f=f, g=pa.IndConsensus(5), gamma=gamma)
+    u = f.image(y)
+    assert k < 3000 and f.objective(u) < f.objective(b)
+    with pytest.raises(ValueError):
+        next(iter(pa.DouglasRachfordIteration(x0, f=f, g=pa.IndConsensus(4), gamma=gamma)))

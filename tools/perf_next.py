@@ -117,6 +117,18 @@ def main():
     gd = pa.NormL1(0.3).descriptor(np.float32)
     x1 = torch.empty_like(x0)
     rec("k8_dr_step_8192sq", timeit(lambda: L.check(ctx.lib.pb_dr_step(ctx.h, L.PB_F32, npx, ptr(x0), 0.7, C.byref(fd), C.byref(gd), ptr(x1), None, None, None, None)), reps=50), 3 * es * npx)
+    sweep = []
+    for unroll in (1, 2, 4):
+        for ctas in (1, 2, 3, 4, 6, 8):
+            ctx.set_launch(ctas_per_sm=ctas, unroll=unroll)
+            ms = timeit(lambda: L.check(ctx.lib.pb_dr_step(ctx.h, L.PB_F32, npx, ptr(x0), 0.7, C.byref(fd), C.byref(gd), ptr(x1), None, None, None, None)), reps=30)
+            sweep.append(dict(unroll=unroll, ctas_per_sm=ctas, ms=ms, frac=3 * es * npx / ms / 1e6 / PEAK))
+    ctx.set_launch()
+    out["k8_dr_step_sweep"] = sweep
+    print("k8 sweep", sorted(sweep, key=lambda r: r["ms"])[:6], flush=True)
+    gd2 = pa.IndBox(-0.5, 0.5).descriptor(np.float32)
+    fd2 = pa.NormL1(0.3).descriptor(np.float32)
+    rec("k8_dr_step_8192sq_l1_box_inplace", timeit(lambda: L.check(ctx.lib.pb_dr_step(ctx.h, L.PB_F32, npx, ptr(x0), 0.7, C.byref(fd2), C.byref(gd2), ptr(x0), None, None, None, None)), reps=50), 2 * es * npx)
     K = 200
     alg = pa.DouglasRachford(maxit=K, tol=-1.0)
     alg(x0=x0, f=pa.SqrNormL2(1.0, bimg), g=pa.NormL1(0.3), gamma=0.7)
