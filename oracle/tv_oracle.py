@@ -13,9 +13,9 @@ prox is the exact minimiser of its two-variable problem, the fixed point satisfi
     DR on X = (x_0..x_4):  F(X) = sum_k f_k(x_k) (class TVSplit),  G = indicator{x_0 = ... = x_4} (class Consensus)
 
 Arithmetic (element type T, every operation rounded separately, same order as csrc/tv_kernels.cu):
-    data:  (x - b)/(1 + gamma) + b
+    data:  (x - b)*w + b,  w = 1/(1 + gamma) rounded once
     pair:  d = a - c; t = gamma*lam;  |d| <= 2t -> (a + c)*0.5 for both, else a - copysign(t, d)
-    mean:  ((((r0 + r1) + r2) + r3) + r4)/5
+    mean:  ((((r0 + r1) + r2) + r3) + r4)*0.2
 """
 from __future__ import annotations
 
@@ -49,8 +49,8 @@ class TVSplit:
         x = X.reshape(5, H, W)
         y = x.copy()
         t = T(T(gamma) * T(self.lam))
-        den = T(T(1) + T(gamma))
-        y[0] = ((x[0] - self.b) / den + self.b).astype(T)
+        w = T(T(1) / T(T(1) + T(gamma)))
+        y[0] = ((x[0] - self.b) * w + self.b).astype(T)
         # horizontal pairs: even (0,1),(2,3)...; odd (1,2),(3,4)...
         for k, start in ((1, 0), (2, 1)):
             a, c = x[k][:, start:W - 1:2], x[k][:, start + 1:W:2]
@@ -86,7 +86,7 @@ class Consensus:
         s = r[0].copy()
         for k in range(1, self.K):
             s = (s + r[k]).astype(T)
-        z = (s / T(self.K)).astype(T)
+        z = (s * T(1.0 / self.K)).astype(T)
         return np.tile(z, self.K), T(0)
 
 

@@ -4,13 +4,13 @@
 //
 // Total variation is not in the reference (nor is any TV prox in its tests); the splitting is ours and the oracle for it is
 // oracle/tv_oracle.py.  The objective is a sum of five terms whose proxes are closed-form and embarrassingly parallel:
-//   f_0 = 0.5||u - b||^2                       prox: (x - b)/(1 + gamma) + b
+//   f_0 = 0.5||u - b||^2                       prox: (x - b)*w + b with w = 1/(1 + gamma) rounded once (no per-pixel divide)
 //   f_1 / f_2 = lambda * sum over the EVEN / ODD horizontal pairs (j, j+1) of |u_j+1 - u_j|
 //   f_3 / f_4 = lambda * sum over the EVEN / ODD vertical pairs (i, i+1)
 //   (pairs of one set are disjoint, so the prox acts on each pair alone: with d = a - c and t = gamma*lambda,
 //    |d| <= 2t -> both become (a + c)/2, otherwise a - sign(d) t and c + sign(d) t)
 // DR runs on X = (x_0..x_4) with F(X) = sum_k f_k(x_k) and G = indicator{x_0 = ... = x_4} (prox = average of the copies):
-//   y_k = prox_{gamma f_k}(x_k);  r_k = 2 y_k - x_k;  z = (r_0 + ... + r_4)/5;  res_k = y_k - z;  x_k <- x_k - res_k.
+//   y_k = prox_{gamma f_k}(x_k);  r_k = 2 y_k - x_k;  z = (r_0 + ... + r_4)*0.2;  res_k = y_k - z;  x_k <- x_k - res_k.
 //
 // The kernel does the WHOLE iteration in one pass over the image: read the five copies and b, write the five copies
 // (11 image passes = 44 B/pixel in Float32; the reference sequence of five broadcasts would move 5 x 13 vectors).  The pair
@@ -35,7 +35,7 @@ struct TvParams {
   const void* halo_prev;   // row (row0 - 1) of the copy that pairs it with row0, or NULL
   const void* halo_next;   // row (row0 + H) of the copy that pairs it with row0 + H - 1, or NULL
   int64_t H, W, row0, Hglob;
-  double t, den;      // gamma*lambda and 1 + gamma, in the element type
+  double t, w;        // gamma*lambda and 1/(1 + gamma), in the element type
   PbWorkspace* ws;
   double* outs;
   XchgParams xchg;
@@ -48,8 +48,10 @@ __device__ __forceinline__ T tv_pair(T a, T c, T t, T t2) {
   return sub_rn(a, copysign(t, d));
 }
 
-template <typename T, int VEC>
-__global__ void __launch_bounds__(PB_BLOCK) k_dr_tv(TvParams p) {
+// MINB: CTAs per SM the register allocation must allow (the pass is latency-bound at 2: ncu shows 16 warps/SM stalled on the
+// long scoreboard; 3-4 trade a few spills for more loads in flight)
+template <typename T, int VEC, int MINB>
+__global__ void __launch_bounds__(PB_BLOCK, MINB) k_dr_tv(TvParams p) {
   const T* __restrict__ x = static_cast<const T*>(p.x);
   const T* __restrict__ b = static_cast<const T*>(p.b);
   const T* __restrict__ hp = static_cast<const T*>(p.halo_prev);
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_dr_tv(TvParams p) {
   T* __restrict__ yo = static_cast<T*>(p.y);
   T* __restrict__ zo = static_cast<T*>(p.z);
   const int64_t H = p.H, W = p.W, HW = H * W;
-  const T t = (T)p.t, t2 = mul_rn(T(2), t), den = (T)p.den;
+  const T t = (T)p.t, t2 = mul_rn(T(2), t), w = (T)p.w;
   T mx = T(0);
   const int64_t npacks = HW / VEC;              // W % VEC == 0 (launcher)
   for (int64_t q = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; q < npacks; q += (int64_t)gridDim.x * PB_BLOCK) {
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_dr_tv(TvParams p) {
     for (int e = 0; e < VEC; ++e) {
       const int par = VEC == 1 ? (int)(j0 & 1) : (e & 1);       // parity of the column (j0 is even when VEC > 1)
       T y[5];
-      y[0] = add_rn(sub_rn(xv[0].v[e], bv.v[e]) / den, bv.v[e]);
+      y[0] = add_rn(mul_rn(sub_rn(xv[0].v[e], bv.v[e]), w), bv.v[e]);
       {  // even horizontal pairs: partner is column j ^ 1
         T c = T(0);
         bool has;
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_dr_tv(TvParams p) {
       T r[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) r[k] = sub_rn(mul_rn(T(2), y[k]), xv[k].v[e]);
-      const T zz = add_rn(add_rn(add_rn(add_rn(r[0], r[1]), r[2]), r[3]), r[4]) / T(5);
+      const T zz = mul_rn(add_rn(add_rn(add_rn(add_rn(r[0], r[1]), r[2]), r[3]), r[4]), T(0.2));
       zv.v[e] = zz;
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
@@ -185,11 +187,13 @@ extern "C" int pb_dr_tv_step(pb_ctx* ctx, int dtype, int64_t H, int64_t W, const
   if (dtype == PB_F32) {
     p.t = (double)mul_rn_host((float)gamma, (float)lambda);
     volatile float den = 1.0f + (float)gamma;
-    p.den = (double)den;
+    volatile float w = 1.0f / den;
+    p.w = (double)w;
   } else {
     p.t = mul_rn_host(gamma, lambda);
     volatile double den = 1.0 + gamma;
-    p.den = den;
+    volatile double w = 1.0 / den;
+    p.w = w;
   }
   pb_xchg_next(ctx, &p.xchg, ctx->xchg_fused != 0 && H * W > 0);
   const int vec = dtype == PB_F32 ? 4 : 2;
@@ -198,16 +202,27 @@ extern "C" int pb_dr_tv_step(pb_ctx* ctx, int dtype, int64_t H, int64_t W, const
   bool vec_ok = W % vec == 0 && ((size_t)H * W * es) % 16 == 0;
   for (const void* q : ptrs) vec_ok = vec_ok && (!q || pb_aligned16(q));
   const int64_t n = H * W;
+  const int minb = ctx->ctas_per_sm == 2 || ctx->ctas_per_sm == 4 ? ctx->ctas_per_sm : 3;
+  const int grid_v = (int)((int64_t)ctx->sm_count * minb < (n / (PB_BLOCK * vec) + 1) ? (int64_t)ctx->sm_count * minb
+                                                                                         : (n / (PB_BLOCK * vec) + 1));
   if (dtype == PB_F32) {
-    if (vec_ok)
-      k_dr_tv<float, 4><<<pb_stream_grid(ctx, PB_BLOCK * 4, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+    if (!vec_ok)
+      k_dr_tv<float, 1, 2><<<pb_stream_grid(ctx, PB_BLOCK, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+    else if (minb == 2)
+      k_dr_tv<float, 4, 2><<<grid_v, PB_BLOCK, 0, ctx->stream>>>(p);
+    else if (minb == 3)
+      k_dr_tv<float, 4, 3><<<grid_v, PB_BLOCK, 0, ctx->stream>>>(p);
     else
-      k_dr_tv<float, 1><<<pb_stream_grid(ctx, PB_BLOCK, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+      k_dr_tv<float, 4, 4><<<grid_v, PB_BLOCK, 0, ctx->stream>>>(p);
   } else {
-    if (vec_ok)
-      k_dr_tv<double, 2><<<pb_stream_grid(ctx, PB_BLOCK * 2, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+    if (!vec_ok)
+      k_dr_tv<double, 1, 2><<<pb_stream_grid(ctx, PB_BLOCK, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+    else if (minb == 2)
+      k_dr_tv<double, 2, 2><<<grid_v, PB_BLOCK, 0, ctx->stream>>>(p);
+    else if (minb == 3)
+      k_dr_tv<double, 2, 3><<<grid_v, PB_BLOCK, 0, ctx->stream>>>(p);
     else
-      k_dr_tv<double, 1><<<pb_stream_grid(ctx, PB_BLOCK, n, 4), PB_BLOCK, 0, ctx->stream>>>(p);
+      k_dr_tv<double, 2, 4><<<grid_v, PB_BLOCK, 0, ctx->stream>>>(p);
   }
   PB_LAUNCH_CHECK(ctx);
   return PB_OK;

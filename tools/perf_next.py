@@ -140,6 +140,32 @@ def main():
     out["config4shape_dr_solver_elementwise"] = dict(iterations=k, ms_per_iteration=1e3 * dt / k, it_per_s=k / dt, gbs=3 * es * npx * k / dt / 1e9,
                                                      frac=3 * es * npx * k / dt / 1e9 / PEAK, note="includes x0 copy, per-iteration scalar read-back, final y materialisation")
     print(out["config4shape_dr_solver_elementwise"], flush=True)
+    del x0, x1, bimg, yv
+    torch.cuda.empty_cache()
+    # ---- configs[4]: TV denoising of the 8192 x 8192 image, consensus-form Douglas-Rachford, one fused pass per iteration (K10) ----
+    bt = torch.randn(side, side, device="cuda")
+    ftv = pa.TVSplit(bt, 0.3)
+    X0 = ftv.initial_point()
+    X1 = torch.empty_like(X0)
+    rec("k10_dr_tv_step_8192sq", timeit(lambda: L.check(ctx.lib.pb_dr_tv_step(ctx.h, L.PB_F32, side, side, ptr(X0), ptr(ftv.b), 1.0, 0.3, ptr(X1), None, None, 0, side, None, None)), reps=20), 11 * es * npx)
+    for ctas in (2, 3, 4):
+        ctx.set_launch(ctas_per_sm=ctas)
+        ms = timeit(lambda: L.check(ctx.lib.pb_dr_tv_step(ctx.h, L.PB_F32, side, side, ptr(X0), ptr(ftv.b), 1.0, 0.3, ptr(X1), None, None, 0, side, None, None)), reps=10)
+        print("k10 ctas_per_sm", ctas, ms, 11 * es * npx / ms / 1e6 / PEAK, flush=True)
+        out.setdefault("k10_sweep", []).append(dict(ctas_per_sm=ctas, ms=ms, frac=11 * es * npx / ms / 1e6 / PEAK))
+    ctx.set_launch()
+    del X1
+    K = 100
+    alg = pa.DouglasRachford(maxit=K, tol=-1.0)
+    alg(x0=X0, f=ftv, g=pa.IndConsensus(5), gamma=1.0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    yv, k = alg(x0=X0, f=ftv, g=pa.IndConsensus(5), gamma=1.0)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["config4_tv_dr_solver"] = dict(iterations=k, ms_per_iteration=1e3 * dt / k, it_per_s=k / dt, gbs=11 * es * npx * k / dt / 1e9,
+                                       frac=11 * es * npx * k / dt / 1e9 / PEAK, note="includes x0 copy, per-iteration scalar read-back, final y/z materialisation")
+    print(out["config4_tv_dr_solver"], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "perf_next.json"), "w"), indent=1)
 
