@@ -222,6 +222,10 @@ int pb_lbfgs_apply(pb_ctx* ctx, pb_lbfgs* op, const void* v, double scale, void*
 int pb_dr_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, double gamma, const pb_prox* f, const pb_prox* g,
                void* x_out, void* y, void* r, void* z, void* res);
 
+/* prox!(out, convex_conjugate(h), v, gamma) by the Moreau identity out = v - gamma*prox_{h/gamma}(v/gamma) (ProximalCore;
+ * call site src/algorithms/primal_dual.jl:195) for the element-wise kinds; Zero* = IndZero gives out = 0. */
+int pb_conj_prox(pb_ctx* ctx, int dtype, int64_t n, const void* v, double gamma, const pb_prox* h, void* out);
+
 /* ---- K10: Douglas-Rachford iteration of anisotropic TV denoising in consensus form (BASELINE.json configs[4]) -------
  * minimize 0.5*||u - b||^2 + lambda*TV(u) split into five terms (data, even/odd horizontal pairs, even/odd vertical
  * pairs) on five stacked copies x[5][H][W] (row-major images); one call = one whole iteration of

@@ -110,6 +110,7 @@ SIGNATURES = {
     "pb_lbfgs_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pb_lbfgs_commit": (_i, [_vp, _d, _d, C.POINTER(C.c_int)]),
     "pb_lbfgs_apply": (_i, [_vp, _vp, _vp, _d, _vp, _vp, _vp]),
+    "pb_conj_prox": (_i, [_vp, _i, _i64, _vp, _d, _pp, _vp]),
     "pb_dr_tv_step": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _d, _d, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "pb_ipc_export": (_i, [_vp, _vp, _vp]),
     "pb_ipc_open": (_i, [_vp, _vp, C.POINTER(_vp)]),

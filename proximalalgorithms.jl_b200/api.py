@@ -31,6 +31,7 @@ from .functions import (  # noqa: F401
     SquaredDistance,
     Zero,
 )
+from .primal_dual import AFBA, AFBAIteration, ChambollePock, ChambollePockIteration, VuCondat, VuCondatIteration  # noqa: F401
 from .tv import IndConsensus, TVSplit  # noqa: F401
 from .panoc import PANOC, PANOCIteration, PANOCState  # noqa: F401
 from . import iteration_tools as IterationTools  # noqa: F401

@@ -290,3 +290,50 @@ int pb_prox_sqrl2_apply(pb_ctx* ctx, int dtype, int64_t n, const void* y, double
   PB_LAUNCH_CHECK(ctx);
   return PB_OK;
 }
+
+// ---- prox of a convex conjugate by the Moreau identity (ProximalCore ConvexConjugate; primal_dual.jl:195) -------------------
+// out = v - gamma * prox_{h/gamma}(v/gamma) for the element-wise kinds; Zero* = IndZero -> out = 0.  One pass (2 vectors).
+template <typename T>
+__global__ void __launch_bounds__(PB_BLOCK) k_conj_prox(const T* __restrict__ v, T* __restrict__ out, int64_t n, DrProx d,
+                                                        double gamma_d, int zero_conj) {
+  const T gamma = (T)gamma_d;
+  const T* __restrict__ v0 = static_cast<const T*>(d.v0);
+  const T* __restrict__ v1 = static_cast<const T*>(d.v1);
+  for (int64_t i = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * PB_BLOCK) {
+    if (zero_conj) {
+      out[i] = T(0);
+      continue;
+    }
+    const T vv = v[i];
+    const T p = dr_prox<T, -1>(d, vv / gamma, v0 ? v0[i] : T(0), v1 ? v1[i] : T(0));
+    out[i] = sub_rn(vv, mul_rn(gamma, p));
+  }
+}
+
+extern "C" int pb_conj_prox(pb_ctx* ctx, int dtype, int64_t n, const void* v, double gamma, const pb_prox* h, void* out) {
+  PB_REQUIRE(ctx != nullptr, "null context");
+  PB_REQUIRE(dtype == PB_F32 || dtype == PB_F64, "dtype must be PB_F32 or PB_F64");
+  PB_REQUIRE(n >= 0, "negative length");
+  PB_REQUIRE(h != nullptr, "null prox descriptor");
+  PB_REQUIRE(n == 0 || (v && out), "null vector");
+  PB_REQUIRE(gamma > 0, "gamma must be positive");
+  DrProx d;
+  int rc;
+  // the inner prox runs with parameter 1/gamma, formed in the element type
+  if (dtype == PB_F32) {
+    volatile float ig = 1.0f / (float)gamma;
+    rc = dr_fill<float>(&d, h, (double)ig);
+  } else {
+    volatile double ig = 1.0 / gamma;
+    rc = dr_fill<double>(&d, h, ig);
+  }
+  if (rc != PB_OK) return rc;
+  const int grid = pb_stream_grid(ctx, PB_BLOCK * 4, n, 4);
+  const int zc = h->kind == PB_PROX_ZERO;
+  if (dtype == PB_F32)
+    k_conj_prox<float><<<grid, PB_BLOCK, 0, ctx->stream>>>((const float*)v, (float*)out, n, d, gamma, zc);
+  else
+    k_conj_prox<double><<<grid, PB_BLOCK, 0, ctx->stream>>>((const double*)v, (double*)out, n, d, gamma, zc);
+  PB_LAUNCH_CHECK(ctx);
+  return PB_OK;
+}

@@ -340,6 +340,18 @@ class EmuLib:
             _vec(x_d, n, dt)[...] = (_vec(x, n, dt) + dv).astype(T)
         return 0
 
+    def pb_conj_prox(self, h, dt, n, v, gamma, hd, out):
+        T = np.float32 if dt == L.PB_F32 else np.float64
+        self.launches += 1
+        hd_ = hd._obj if hasattr(hd, "_obj") else hd
+        vv = _vec(v, n, dt).copy()
+        if hd_.kind == L.PB_PROX_ZERO:
+            _vec(out, n, dt)[...] = 0
+            return 0
+        p = self._prox(T, hd_, (vv / T(gamma)).astype(T), T(T(1) / T(gamma)), set_gsum=False)
+        _vec(out, n, dt)[...] = (vv - (T(gamma) * p).astype(T)).astype(T)
+        return 0
+
     # ---- K9: least-squares prox ---------------------------------------------------------------------------------------
     def pb_lsq_prox_create(self, h, dt, m, n, A, b, lam, out):
         key = self._next

@@ -14,6 +14,7 @@ Sources (all paths relative to /root/reference):
     b = A x* + lam inv(A') sign(x*), x0 = A \\ b are re-derived with LAPACK exactly as the test does.
   * test/accel/test_lbfgs.jl:6-101 -- literal Q, q, xs and the five reference L-BFGS directions.
   * test/problems/test_sparse_logistic_small.jl:34 -- literal x_star.
+  * test/problems/test_elasticnet.jl:27 -- literal x_star.
 The literals are parsed out of the .jl files with regular expressions (nothing is copied by hand).
 """
 import hashlib
@@ -120,6 +121,14 @@ def unit_sparse_logistic():
     return dict(xstar=xs, lam=np.float64(0.1))
 
 
+def unit_elasticnet():
+    """test/problems/test_elasticnet.jl:27 literal x_star (A, b are those of the 4x5 Lasso; ElasticNet(1, 1))."""
+    src = open(os.path.join(REF, "test", "problems", "test_elasticnet.jl")).read()
+    xs = _vector(_block_after(src, "x_star = T["))
+    assert xs.shape == (5,)
+    return dict(xstar=xs)
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not present: golden fixtures can only be regenerated in the build container")
@@ -132,6 +141,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "unit_lasso_sc_5x5.npz"), **unit_lasso_sc_5x5())
     np.savez_compressed(os.path.join(OUT, "lbfgs_known_answers.npz"), **lbfgs_known_answers())
     np.savez_compressed(os.path.join(OUT, "unit_sparse_logistic.npz"), **unit_sparse_logistic())
+    np.savez_compressed(os.path.join(OUT, "unit_elasticnet.npz"), **unit_elasticnet())
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 

@@ -9,6 +9,7 @@ import torch
 import proxb200 as pa
 from oracle import fb_oracle as o
 from oracle import panoc_oracle as po
+from oracle import afba_oracle as ao
 from oracle import tv_oracle as tvo
 from proxb200 import algorithms, functions, host
 
@@ -213,3 +214,49 @@ def test_tv_douglas_rachford_host_logic(emu, T):
     assert k < 3000 and f.objective(u) < f.objective(b)
     with pytest.raises(ValueError):
         next(iter(pa.DouglasRachfordIteration(x0, f=f, g=pa.IndConsensus(4), gamma=gamma)))
+
+
+def _afba_cases(golden, T):
+    A, b, lam, xstar = _lasso_4x5(golden, T)
+    beta_f = T(np.linalg.norm(A, 2) ** 2)
+    xs_en = golden("unit_elasticnet")["xstar"].astype(T)
+    z5, z4 = np.zeros(5, T), np.zeros(4, T)
+    cases = [
+        ("lasso_g", dict(x0=z5, y0=z5, f=o.LeastSquares(A, b), g=o.NormL1(lam), beta_f=beta_f, theta=1, mu=1),
+         dict(x0=z5, y0=z5, f=pa.LeastSquares(A, b), g=pa.NormL1(lam), beta_f=beta_f, theta=1, mu=1), xstar, 80),
+        ("lasso_h", dict(x0=z5, y0=z5, f=o.LeastSquares(A, b), h=o.NormL1(lam), beta_f=beta_f, theta=1, mu=1),
+         dict(x0=z5, y0=z5, f=pa.LeastSquares(A, b), h=pa.NormL1(lam), beta_f=beta_f, theta=1, mu=1), xstar, 100),
+        ("lasso_L", dict(x0=z5, y0=z4, h=po.SqrNormL2Translated(b, 1.0), L=A, g=o.NormL1(lam), theta=1, mu=1),
+         dict(x0=z5, y0=z4, h=pa.SqrNormL2(1.0, b), L=A, g=pa.NormL1(lam), theta=1, mu=1), xstar, 150),
+    ]
+    for theta, mu, maxit in [(2, 0, 130), (1, 1, 2000), (0, 1, 320), (0, 0, 194), (1, 0, 130)]:
+        cases.append((f"enet_{theta}_{mu}",
+                      dict(x0=z5, y0=z4, f=ao.SqrNormL2Smooth(1.0), g=o.NormL1(T(1)), h=po.SqrNormL2Translated(b, 1.0), L=A, beta_f=1, theta=theta, mu=mu),
+                      dict(x0=z5, y0=z4, f=pa.SqrNormL2(1.0), g=pa.NormL1(1.0), h=pa.SqrNormL2(1.0, b), L=A, beta_f=1, theta=theta, mu=mu), xs_en, maxit))
+    return cases
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_afba_host_logic_matches_oracle(emu, golden, T):
+    # test/problems/test_lasso_small.jl:233-275 and test_elasticnet.jl:56-113 on the product's host logic
+    for name, kw_o, kw_p, xstar, bound in _afba_cases(golden, T):
+        it_o, it_p = ao.AFBAIteration(**kw_o), pa.AFBAIteration(**kw_p)
+        assert it_p.gamma == it_o.gamma, name
+        for k, (so, sp) in enumerate(zip(it_o, it_p)):
+            tol = 1e-12 if T is np.float64 else 1e-5
+            assert np.max(np.abs(sp.xbar.numpy() - so.xbar)) <= tol and np.max(np.abs(sp.ybar.numpy() - so.ybar)) <= tol, (name, k)
+            assert np.max(np.abs(sp.x.numpy() - so.x)) <= tol and np.max(np.abs(sp.y.numpy() - so.y)) <= tol, (name, k)
+            assert np.max(np.abs(sp.FPR_x.numpy() - so.FPR_x)) <= tol
+            if k == 10:
+                break
+        (x, y), it = pa.AFBA(tol=T(1e-6), **{k_: v for k_, v in kw_p.items() if k_ in ("theta", "mu")})(**{k_: v for k_, v in kw_p.items() if k_ not in ("theta", "mu")})
+        (xo, yo), ito = ao.afba(tol=T(1e-6), **kw_o)
+        assert x.dtype == T and y.dtype == T and np.max(np.abs(x - xstar)) <= 1e-4 and it <= bound, (name, it)
+        assert abs(it - ito) <= max(2, ito // 20), (name, it, ito)
+    A, b, lam, xstar = _lasso_4x5(golden, T)
+    (x, y), it = pa.ChambollePock(tol=T(1e-6))(x0=np.zeros(5, T), y0=np.zeros(4, T), h=pa.SqrNormL2(1.0, b), L=A, g=pa.NormL1(lam))
+    assert np.max(np.abs(x - xstar)) <= 1e-4
+    with pytest.raises(ValueError):
+        pa.AFBAIteration(np.zeros(5, T), np.zeros(5, T), f=pa.LeastSquares(A, b))
+    with pytest.raises(ValueError):
+        pa.AFBAIteration(np.zeros(5, T), np.zeros(5, T), lambda_=0.5)
