@@ -286,6 +286,13 @@ typedef struct pb_solve_opts {
   double mf;             /* convexity modulus seeding AdaptiveNesterovSequence                                  */
   double constant_beta;  /* value of PB_SEQ_CONSTANT                                                            */
   double minimum_gamma, reduce_gamma, increase_gamma;
+  /* Optional pipelining of the fixed-stepsize FFB loop (all three non-NULL, device exchange attached): the kernel of
+   * iteration k+1 is launched BEFORE the host has received the scalars of iteration k, so the host-side stop test, the
+   * exchange latency and the launch overhead hide behind the next kernel.  Iteration k+1 only reads what iteration k
+   * wrote and writes into these spare n-vectors, so when the stop test of iteration k fires the state of iteration k is
+   * intact (x, grad, z, z_prev as reported in pb_solve_result) and one speculative launch is discarded.  Results
+   * (iterates, scalars, iteration count) are identical to the unpipelined loop. */
+  void *spare_x, *spare_z, *spare_grad;
 } pb_solve_opts;
 
 typedef struct pb_solve_result {

@@ -41,7 +41,8 @@ class pb_smooth(C.Structure):
 class pb_solve_opts(C.Structure):
     _fields_ = [("algorithm", C.c_int32), ("adaptive", C.c_int32), ("sequence", C.c_int32), ("profile", C.c_int32),
                 ("maxit", C.c_int64), ("n_global", C.c_int64), ("tol", C.c_double), ("gamma", C.c_double), ("mf", C.c_double),
-                ("constant_beta", C.c_double), ("minimum_gamma", C.c_double), ("reduce_gamma", C.c_double), ("increase_gamma", C.c_double)]
+                ("constant_beta", C.c_double), ("minimum_gamma", C.c_double), ("reduce_gamma", C.c_double), ("increase_gamma", C.c_double),
+                ("spare_x", C.c_void_p), ("spare_z", C.c_void_p), ("spare_grad", C.c_void_p)]
 
 
 class pb_solve_result(C.Structure):

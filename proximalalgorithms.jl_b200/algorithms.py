@@ -501,11 +501,18 @@ def _native_solve(alg, it):
     z_prev = t.empty_like(x) if fast else None
     x_next = t.empty_like(x) if fast and not it.adaptive else None
     grad_z = t.empty_like(x) if (not fast and it.adaptive) else None
-    bufs = {b.data_ptr(): b for b in (x, grad, z, scratch, z_prev, x_next, grad_z) if b is not None}
+    # fixed-stepsize FFB through the device exchange: two spare vectors let pb_solve launch iteration k+1 before the scalars of
+    # iteration k have reached the host (pb_solve_opts.spare_*); `scratch` doubles as the spare gradient buffer
+    pipelined = fast and not it.adaptive and isinstance(e.comm, DeviceExchangeComm) and getattr(alg, "pipeline", True)
+    spare_x = t.empty_like(x) if pipelined else None
+    spare_z = t.empty_like(x) if pipelined else None
+    bufs = {b.data_ptr(): b for b in (x, grad, z, scratch, z_prev, x_next, grad_z, spare_x, spare_z) if b is not None}
     n_glob = it.n_global if it.n_global is not None else n * e.comm.size
     opts = L.pb_solve_opts(L.PB_ALG_FFB if fast else L.PB_ALG_FB, 1 if it.adaptive else 0, seq[0], 1 if getattr(alg, "profile", False) else 0, alg.maxit, int(n_glob), float(tol),
                            0.0 if it.gamma is None else float(R(it.gamma)), float(getattr(it, "mf", 0.0)), seq[1],
-                           float(it.minimum_gamma), float(it.reduce_gamma), float(it.increase_gamma))
+                           float(it.minimum_gamma), float(it.reduce_gamma), float(it.increase_gamma),
+                           spare_x.data_ptr() if pipelined else None, spare_z.data_ptr() if pipelined else None,
+                           scratch.data_ptr() if pipelined else None)
     gdesc = g.descriptor(R)
     res = L.pb_solve_result()
     t1 = time.perf_counter()

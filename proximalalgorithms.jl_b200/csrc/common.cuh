@@ -48,7 +48,7 @@ struct pb_ctx {
   // C1 exchange (xchg.cu): own IPC-exported buffer, peer mappings, mapped pinned landing zone for the host
   unsigned long long* xchg_own;
   unsigned long long* xchg_peer[PB_MAX_RANKS];
-  unsigned long long* xchg_host_words;      // host pointer (pinned, mapped): [world][32] words
+  unsigned long long* xchg_host_words;      // host pointer (pinned, mapped): [parity][PB_MAX_RANKS][32] words
   unsigned long long* xchg_host_words_dev;  // its device alias
   unsigned int xchg_seq;                    // last sequence number issued
   int xchg_rank, xchg_world;                // world == 0: not initialised
@@ -60,6 +60,8 @@ struct pb_ctx {
 
 // Fill the kernel-side parameters for the next in-kernel exchange (advances the sequence number); world = 0 if disabled.
 void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want);
+// Wait for one specific exchange (by sequence number) in the pinned landing zone; rows_out: world x PB_NSCALARS doubles.
+int pb_xchg_wait_seq(pb_ctx* ctx, unsigned int seq, double* rows_out, double timeout_s);
 
 void pb_set_error(const char* fmt, ...);
 int pb_ensure_scratch(pb_ctx* ctx, size_t bytes);

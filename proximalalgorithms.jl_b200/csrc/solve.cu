@@ -73,6 +73,21 @@ int read_comb(pb_ctx* ctx, Comb* c) {
   return PB_OK;
 }
 
+// Same, for one specific exchange of the pipelined loop (sequence number recorded right after the publishing launch).
+int read_comb_seq(pb_ctx* ctx, unsigned int seq, Comb* c) {
+  double rows[PB_MAX_RANKS * PB_NSCALARS];
+  const int world = ctx->xchg_world, rank = ctx->xchg_rank;
+  int rc = pb_xchg_wait_seq(ctx, seq, rows, 30.0);
+  if (rc != PB_OK) return rc;
+  c->gsum = fold(rows, world, PB_S_GSUM);
+  c->res_sq = fold(rows, world, PB_S_RESSQ);
+  c->gdr = fold(rows, world, PB_S_GDR);
+  c->aux = fold(rows, world, PB_S_AUX);
+  c->res_inf = fold_max(rows, world, PB_S_RESINF);
+  c->local_aux = rows[rank * PB_NSCALARS + PB_S_AUX] + rows[rank * PB_NSCALARS + PB_S_AUX + 1];
+  return PB_OK;
+}
+
 // square root IN R (numpy's sqrt of an R scalar): sqrtf for float, sqrt for double
 inline float rs(float v) { return sqrtf(v); }
 inline double rs(double v) { return sqrt(v); }
@@ -199,10 +214,11 @@ struct Solver {
     if (f->kind == PB_F_LSQ_DENSE || f->kind == PB_F_LSQ_BLOCKDIAG) return residual(v);
     return eval_f(v, scratch);
   }
-  int step(const void* xin, const void* gr, void* zout, bool extrap, R beta) {
+  int step(const void* xin, const void* gr, void* zout, bool extrap, R beta) { return step_to(xin, gr, z_prev, zout, x_next, extrap, beta); }
+  int step_to(const void* xin, const void* gr, const void* zp, void* zout, void* xnext_out, bool extrap, R beta) {
     const bool timed = profile && n_step_events < kMaxStepEvents;
     if (timed) cudaEventRecord(ev_step[2 * n_step_events], ctx->stream);
-    const int rc = extrap ? pb_ffb_step(ctx, dtype, n, xin, gr, z_prev, (double)gamma, (double)beta, g, nullptr, zout, nullptr, x_next)
+    const int rc = extrap ? pb_ffb_step(ctx, dtype, n, xin, gr, zp, (double)gamma, (double)beta, g, nullptr, zout, nullptr, xnext_out)
                           : pb_fb_step(ctx, dtype, n, xin, gr, (double)gamma, g, nullptr, zout, nullptr);
     if (timed) {
       cudaEventRecord(ev_step[2 * n_step_events + 1], ctx->stream);
@@ -321,6 +337,9 @@ struct Solver {
       rc = step(x, grad, z, false, R(0));
     }
     if (rc) return rc;
+    const bool pipelined = fast && !adaptive && o->spare_x && o->spare_z && o->spare_grad && ctx->xchg_world > 0 &&
+                           ctx->xchg_connected && ctx->xchg_fused && n > 0;
+    if (pipelined) return run_ffb_pipelined(out, seq, beta_next);
     if ((rc = read_comb(ctx, &sc))) return rc;
     if (fx_pending) f_x = f_value(sc);
     g_z = g_value(sc);
@@ -369,6 +388,63 @@ struct Solver {
         g_z = g_value(sc);
       }
     }
+    return finish(out, k);
+  }
+
+  // Fixed-stepsize FFB with one iteration of look-ahead (pb_solve_opts: spare_x / spare_z / spare_grad).  Invariant at the top of
+  // the loop: the kernel of iteration k has been launched and will publish exchange `seq_k`; X[ix] = x_k, X[ixn] = x_{k+1}
+  // (written by that kernel), Z[izp] = z_{k-1}, Z[iz] = z_k (ditto), G[ig] = grad f(x_k).  The body of iteration k+1 reads
+  // x_{k+1}, z_k and writes the third x / z buffer and the other gradient buffer, so nothing of iteration k is overwritten
+  // before its scalars have been examined.
+  int run_ffb_pipelined(pb_solve_result* out, Nesterov<R>& seq, R beta_next) {
+    int rc;
+    void* X[3] = {x, x_next, o->spare_x};
+    void* Z[3] = {z_prev, z, o->spare_z};
+    void* G[2] = {grad, (f->kind == PB_F_LINEAR && grad == f->b) ? grad : o->spare_grad};
+    int ix = 0, ixn = 1, izp = 0, iz = 1, ig = 0;
+    unsigned int seq_k = ctx->xchg_seq;               // published by the init step launched by the caller
+    (void)beta_next;
+    int64_t k = 1;
+    for (;;) {
+      const bool spec = k < o->maxit;
+      Nesterov<R> seq_saved = seq;
+      unsigned int seq_next = 0;
+      const int ixf = 3 - ix - ixn, izf = 3 - izp - iz, igo = 1 - ig;
+      if (spec) {                                      // fast_forward_backward.jl:130-142 for iteration k+1, launched ahead
+        if ((rc = eval_f_to(X[ixn], G[igo]))) return rc;
+        const R beta = seq.next(gamma);
+        if ((rc = step_to(X[ixn], G[igo], Z[iz], Z[izf], X[ixf], true, beta))) return rc;
+        seq_next = ctx->xchg_seq;
+      }
+      if ((rc = read_comb_seq(ctx, seq_k, &sc))) return rc;
+      f_x = f_value(sc);
+      g_z = g_value(sc);
+      if (k >= o->maxit || stop()) {                   // src/ProximalAlgorithms.jl:117
+        seq = seq_saved;
+        break;
+      }
+      // commit the speculation: iteration k+1 becomes the current one
+      ix = ixn;
+      ixn = ixf;
+      izp = iz;
+      iz = izf;
+      ig = igo;
+      seq_k = seq_next;
+      ++k;
+    }
+    ctx->xchg_pending = 0;                             // whatever was published last has been consumed or is discarded
+    x = X[ix];
+    x_next = X[ixn];
+    z = Z[iz];
+    z_prev = Z[izp];
+    grad = G[ig];
+    return finish(out, k);
+  }
+
+  int eval_f_to(const void* v, void* grad_out) { return eval_f(v, grad_out); }
+
+  int finish(pb_solve_result* out, int64_t k) {
+    int rc;
     if (profile) cudaEventRecord(ev_loop[1], ctx->stream);     // the K iterations end here
     if (lazy_value) {                    // f(x) of the final state (LinearFunction: <c, x>)
       if ((rc = pb_dot(ctx, dtype, n, f->b, x))) return rc;

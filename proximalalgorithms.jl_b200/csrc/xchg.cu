@@ -37,7 +37,7 @@ extern "C" int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out) 
   PB_CHECK_CUDA(cudaMemset(own, 0, PB_XCHG_BYTES));
   ctx->xchg_own = static_cast<unsigned long long*>(own);
   void* host = nullptr;
-  const size_t hbytes = (size_t)PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW * 8;
+  const size_t hbytes = (size_t)2 * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW * 8;   // [parity][rank][word]
   PB_CHECK_CUDA(cudaHostAlloc(&host, hbytes, cudaHostAllocMapped | cudaHostAllocPortable));
   memset(host, 0, hbytes);
   ctx->xchg_host_words = static_cast<unsigned long long*>(host);
@@ -124,9 +124,16 @@ extern "C" int pb_exchange_wait(pb_ctx* ctx, double* rows_out, double timeout_s)
     int rc = pb_exchange(ctx);
     if (rc != PB_OK) return rc;
   }
-  const unsigned int want = ctx->xchg_seq;
+  const int rc = pb_xchg_wait_seq(ctx, ctx->xchg_seq, rows_out, timeout_s);
+  ctx->xchg_pending = 0;
+  return rc;
+}
+
+// Poll the landing zone for exchange `want` (a sequence number handed out by pb_xchg_next).  At most two exchanges may be
+// outstanding: `want` and its successor (different parity slots).
+int pb_xchg_wait_seq(pb_ctx* ctx, unsigned int want, double* rows_out, double timeout_s) {
   const int nwords = ctx->xchg_world * PB_XCHG_WORDS_PER_ROW;
-  volatile unsigned long long* words = ctx->xchg_host_words;
+  volatile unsigned long long* words = ctx->xchg_host_words + (size_t)(want & 1u) * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW;
   unsigned long long got[PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW];
   const double t0 = now_s();
   unsigned long long spins = 0;
@@ -140,12 +147,10 @@ extern "C" int pb_exchange_wait(pb_ctx* ctx, double* rows_out, double timeout_s)
       continue;
     }
     if (s == PB_XCHG_ERROR_SEQ) {
-      ctx->xchg_pending = 0;
       pb_set_error("pb_exchange_wait: a peer did not publish sequence %u within the device time-out", want);
       return PB_ECUDA;
     }
     if ((++spins & 0xfff) == 0 && now_s() - t0 > timeout_s) {
-      ctx->xchg_pending = 0;
       pb_set_error("pb_exchange_wait: timed out after %.1f s waiting for sequence %u (word %d)", timeout_s, want, i);
       return PB_ECUDA;
     }
@@ -157,6 +162,5 @@ extern "C" int pb_exchange_wait(pb_ctx* ctx, double* rows_out, double timeout_s)
     const unsigned long long bits = (got[2 * k] & 0xffffffffull) | ((got[2 * k + 1] & 0xffffffffull) << 32);
     memcpy(&rows_out[k], &bits, 8);
   }
-  ctx->xchg_pending = 0;
   return PB_OK;
 }

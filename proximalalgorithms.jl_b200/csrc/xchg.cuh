@@ -29,7 +29,7 @@
 
 struct XchgParams {
   unsigned long long* peer[PB_MAX_RANKS];   // peer[r]: base of rank r's exchange buffer as mapped in THIS process
-  unsigned long long* host_words;           // device alias of mapped pinned memory: [world][32] words
+  unsigned long long* host_words;           // device alias of mapped pinned memory: [parity][PB_MAX_RANKS][32] words
   unsigned int seq;                         // sequence number of this exchange (never 0, never PB_XCHG_ERROR_SEQ)
   int rank, world;                          // world == 0: exchange disabled
 };
@@ -78,6 +78,7 @@ __device__ __forceinline__ void xchg_push_wait(const XchgParams& xp, const doubl
       v = ld_word(mine);
     }
   }
-  // 3. forward to the host
-  st_word(xp.host_words + t, v);
+  // 3. forward to the host (landing zone double-buffered by parity too, so that the host may still be reading exchange k
+  //    while the kernel of exchange k+1 -- launched ahead by the pipelined driver loop -- publishes)
+  st_word(xp.host_words + (size_t)par * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW + t, v);
 }

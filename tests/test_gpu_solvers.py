@@ -316,3 +316,36 @@ def test_native_driver_equals_python_host(T):
     assert auto.last_driver == "python"
     with pytest.raises(pa.ProxB200Error):
         pa.FastForwardBackward(tol=tol, driver="native")(x0=x0, f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)), Lf=Lf)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_pipelined_native_loop_is_invisible(T):
+    """pb_solve with spare vectors launches iteration k+1 before the scalars of iteration k reach the host (csrc/solve.cu:
+    run_ffb_pipelined).  Same iterations, same bits, same final state as the unpipelined native loop, whether the stop test
+    or maxit ends the run."""
+    d = load_golden("lasso_small")
+    A, b, lam = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T), T(d["lam"])
+    Lf = T(np.linalg.norm(d["A"], 2) ** 2)
+    x0 = np.zeros(A.shape[1], T)
+    rng = np.random.default_rng(1)
+    n = 200_003
+    c, xs = torch.as_tensor(rng.standard_normal(n).astype(T)).cuda(), rng.standard_normal(n).astype(T)
+    problems = [
+        (dict(x0=x0, f=pa.LeastSquares(A, b), g=pa.NormL1(lam), Lf=Lf), T(1e-6 if T == np.float64 else 1e-4), 5000),
+        (dict(x0=x0, f=pa.LeastSquares(A, b), g=pa.NormL1(lam), Lf=Lf), T(-1), 37),
+        (dict(x0=x0, f=pa.LeastSquares(A, b), g=pa.NormL1(lam), Lf=Lf), T(-1), 1),
+        (dict(x0=x0, f=pa.LeastSquares(A, b), g=pa.NormL1(lam), Lf=Lf), T(-1), 2),
+        (dict(x0=xs, f=pa.LinearFunction(c), g=pa.NormL1(T(1)), gamma=T(0.1), extrapolation_sequence=pa.ConstantNesterovSequence(T(0.05), T(1))), T(-1), 25),
+        (dict(x0=xs, f=pa.SquaredDistance(c), g=pa.IndBox(T(-0.5), T(0.5)), gamma=T(0.7)), T(1e-5), 500),
+    ]
+    for kw, tol, maxit in problems:
+        a1, a2 = pa.FastForwardBackward(tol=tol, maxit=maxit, driver="native"), pa.FastForwardBackward(tol=tol, maxit=maxit, driver="native")
+        a2.pipeline = False
+        z1, k1 = a1(**kw)
+        if "extrapolation_sequence" in kw:
+            kw = dict(kw, extrapolation_sequence=pa.ConstantNesterovSequence(T(0.05), T(1)))
+        z2, k2 = a2(**kw)
+        assert k1 == k2 and np.array_equal(z1, z2)
+        s1, s2 = a1.last_state, a2.last_state
+        assert torch.equal(s1.x, s2.x) and torch.equal(s1.z_prev, s2.z_prev) and torch.equal(s1.grad_f_x, s2.grad_f_x)
+        assert s1.f_x == s2.f_x and s1.g_z == s2.g_z and float(s1.res_norm_inf) == float(s2.res_norm_inf)
