@@ -35,6 +35,7 @@ from .primal_dual import AFBA, AFBAIteration, ChambollePock, ChambollePockIterat
 from .tv import IndConsensus, TVSplit  # noqa: F401
 from .panoc import PANOC, PANOCIteration, PANOCState  # noqa: F401
 from . import iteration_tools as IterationTools  # noqa: F401
+from .jld2 import load_lasso_fixture, read_jld2  # noqa: F401
 from .host import Context, DeviceExchangeComm, LocalComm, Scalars, TorchDistComm, shard_bounds  # noqa: F401
 from .nesterov import (  # noqa: F401
     AdaptiveNesterovSequence,

@@ -43,6 +43,13 @@ def read_jld2(name):
     if got != sha:
         raise SystemExit(f"{path}: sha256 {got} != expected {sha}; offsets would be wrong")
     a = np.frombuffer(buf, "<f8", m * n, o_a).reshape(n, m).T  # Julia column-major
+    # cross-check: the package's own HDF5/JLD2 parser (proximalalgorithms.jl_b200/jld2.py) finds the same datasets
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from proxb200 import jld2 as _jld2
+
+    parsed = _jld2.read_jld2(path)
+    assert np.array_equal(parsed["A"], a) and parsed["A"].shape == (m, n) and int(parsed["lambda"]) == int(np.frombuffer(buf, "<i8", 1, o_l)[0])
+    assert np.array_equal(parsed["b"], np.frombuffer(buf, "<f8", m, o_b)) and np.array_equal(parsed["xstar"], np.frombuffer(buf, "<f8", n, o_x))
     return dict(
         A=np.asfortranarray(a),
         b=np.frombuffer(buf, "<f8", m, o_b).copy(),
