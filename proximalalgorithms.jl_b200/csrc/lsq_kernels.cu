@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_gemv_t(const T* __restrict__ A, in
 // grad = A' r for SHORT columns (mb <= 32 lanes x 4 packs): LPC lanes share one column, each lane owns up to KP 16-byte
 // packs of it (rows lane*VEC + k*LPC*VEC), the matching packs of r live in registers for the whole column chunk, a warp
 // handles 32/LPC columns per sweep, log2(LPC) shuffle steps finish a column.  One CTA = one chunk of columns of ONE block.
-template <typename T, int LPC, int KP>
+template <typename T, int LPC, int KP, int SW>
 __global__ void __launch_bounds__(PB_BLOCK) k_gemv_t_sub(const T* __restrict__ A, int64_t lda, int64_t blk_stride,
                                                          const T* __restrict__ r, T* __restrict__ grad, int64_t mb,
                                                          int64_t nb, int64_t chunk_cols, int64_t chunks_per_blk) {
@@ -212,28 +212,39 @@ __global__ void __launch_bounds__(PB_BLOCK) k_gemv_t_sub(const T* __restrict__ A
       for (int e = 0; e < VEC; ++e) rv[q].v[e] = T(0);
   }
   constexpr int WARPS = PB_BLOCK / 32;
-  for (int64_t j = c0 + (int64_t)warp * CPW + colw; j < c1 + colw; j += (int64_t)WARPS * CPW) {
+  // SW column sweeps in flight per thread (independent 16-byte loads): 4 for very short columns (KP <= 2, few registers per
+  // column), 1 for the KP = 4 shapes tuned in profiles/r01_tune_lsq.md
+  const int64_t stride = (int64_t)WARPS * CPW;
+  for (int64_t j0 = c0 + (int64_t)warp * CPW + colw; j0 < c1 + colw; j0 += SW * stride) {
     // (loop bound padded by colw so that all lanes of a warp iterate together; inactive columns contribute nothing)
-    const bool live = j < c1;
-    const T* __restrict__ a = Ak + (live ? j : c0) * lda;
-    Pack<T, VEC> av[KP];
+    Pack<T, VEC> av[SW][KP];
+    bool live[SW];
 #pragma unroll
-    for (int q = 0; q < KP; ++q) {
-      const int64_t pk = sub + (int64_t)q * LPC;
-      if (pk < npk) av[q] = ld_pack<T, VEC, true>(a + pk * VEC);
-    }
-    T acc = T(0);
+    for (int s_ = 0; s_ < SW; ++s_) {
+      const int64_t j = j0 + s_ * stride;
+      live[s_] = j < c1;
+      const T* __restrict__ a = Ak + (live[s_] ? j : c0) * lda;
 #pragma unroll
-    for (int q = 0; q < KP; ++q) {
-      const int64_t pk = sub + (int64_t)q * LPC;
-      if (pk < npk) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) acc = fma(av[q].v[e], rv[q].v[e], acc);
+      for (int q = 0; q < KP; ++q) {
+        const int64_t pk = sub + (int64_t)q * LPC;
+        if (pk < npk) av[s_][q] = ld_pack<T, VEC, true>(a + pk * VEC);
       }
     }
 #pragma unroll
-    for (int off = LPC / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (live && sub == 0) grad[k * nb + j] = acc;
+    for (int s_ = 0; s_ < SW; ++s_) {
+      T acc = T(0);
+#pragma unroll
+      for (int q = 0; q < KP; ++q) {
+        const int64_t pk = sub + (int64_t)q * LPC;
+        if (pk < npk) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc = fma(av[s_][q].v[e], rv[q].v[e], acc);
+        }
+      }
+#pragma unroll
+      for (int off = LPC / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (live[s_] && sub == 0) grad[k * nb + j0 + s_ * stride] = acc;
+    }
   }
 }
 
@@ -265,21 +276,27 @@ static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
   if (rc != PB_OK) return rc;
   T* partial = static_cast<T*>(ctx->scratch);
   constexpr int VEC = 16 / sizeof(T);
-  constexpr int KP = 4;
   const int64_t npk = mb / VEC;
   const bool sub_ok = mb < 64 && mb % VEC == 0 && lda % VEC == 0 && blk_stride % VEC == 0 && pb_aligned16(A) &&
                       nblk * nchunk <= 0x7fffffffLL;
   if (sub_ok) {
+    const int kp = npk <= 1 ? 1 : (npk <= 2 ? 2 : 4);
     int lpc = 1;
-    while ((int64_t)lpc * KP < npk) lpc <<= 1;
-#define PB_LAUNCH_NSUB(L)                                                                                              \
-  k_gemv_n_sub<T, L, KP><<<(unsigned)(nblk * nchunk), PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk, \
-                                                                                 chunk_cols, nchunk)
-    switch (lpc) {
-      case 1: PB_LAUNCH_NSUB(1); break;
-      case 2: PB_LAUNCH_NSUB(2); break;
-      case 4: PB_LAUNCH_NSUB(4); break;
-      default: PB_LAUNCH_NSUB(8); break;
+    while ((int64_t)lpc * kp < npk) lpc <<= 1;
+#define PB_LAUNCH_NSUB(L, KP_)                                                                                              \
+  k_gemv_n_sub<T, L, KP_><<<(unsigned)(nblk * nchunk), PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk, \
+                                                                                  chunk_cols, nchunk)
+    if (kp == 1) {
+      PB_LAUNCH_NSUB(1, 1);
+    } else if (kp == 2) {
+      PB_LAUNCH_NSUB(1, 2);
+    } else {
+      switch (lpc) {
+        case 1: PB_LAUNCH_NSUB(1, 4); break;
+        case 2: PB_LAUNCH_NSUB(2, 4); break;
+        case 4: PB_LAUNCH_NSUB(4, 4); break;
+        default: PB_LAUNCH_NSUB(8, 4); break;
+      }
     }
 #undef PB_LAUNCH_NSUB
   } else {
@@ -300,31 +317,39 @@ static int gradient_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
   const int64_t ncols = nblk * nb;
   if (ncols == 0) return PB_OK;
   constexpr int VEC = 16 / sizeof(T);
-  constexpr int KP = 4;
   const int64_t npk = mb / VEC;
-  const bool sub_ok = mb > 0 && mb % VEC == 0 && lda % VEC == 0 && blk_stride % VEC == 0 && npk <= 32 * KP &&
+  const bool sub_ok = mb > 0 && mb % VEC == 0 && lda % VEC == 0 && blk_stride % VEC == 0 && npk <= 32 * 4 &&
                       pb_aligned16(A) && pb_aligned16(r);
   if (sub_ok) {
+    // packs per lane: 1 or 2 for very short columns (whole column in one lane, 4 columns in flight), else 4 with LPC lanes
+    const int kp = npk <= 1 ? 1 : (npk <= 2 ? 2 : 4);
     int lpc = 1;
-    while ((int64_t)lpc * KP < npk) lpc <<= 1;
-    // chunk the columns of a block so that the grid covers the machine ~8x
-    int64_t chunks = ((int64_t)ctx->sm_count * 8 + nblk - 1) / nblk;
-    const int64_t min_chunk = 256;
+    while ((int64_t)lpc * kp < npk) lpc <<= 1;
+    // chunk the columns of a block so that the grid covers the machine ~8x (~32x for the very short columns, whose CTAs
+    // are cheap: a finer partition shortens the partial last wave)
+    int64_t chunks = ((int64_t)ctx->sm_count * (kp <= 2 ? 32 : 8) + nblk - 1) / nblk;
+    const int64_t min_chunk = kp <= 2 ? 2048 : 256;
     if (chunks > (nb + min_chunk - 1) / min_chunk) chunks = (nb + min_chunk - 1) / min_chunk;
     if (chunks < 1) chunks = 1;
     const int64_t chunk_cols = (nb + chunks - 1) / chunks;
     chunks = (nb + chunk_cols - 1) / chunk_cols;
     const int64_t grid = nblk * chunks;
     PB_REQUIRE(grid <= 0x7fffffffLL, "grid too large");
-#define PB_LAUNCH_SUB(L)                                                                                          \
-  k_gemv_t_sub<T, L, KP><<<(unsigned)grid, PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, r, grad, mb, nb, chunk_cols, chunks)
-    switch (lpc) {
-      case 1: PB_LAUNCH_SUB(1); break;
-      case 2: PB_LAUNCH_SUB(2); break;
-      case 4: PB_LAUNCH_SUB(4); break;
-      case 8: PB_LAUNCH_SUB(8); break;
-      case 16: PB_LAUNCH_SUB(16); break;
-      default: PB_LAUNCH_SUB(32); break;
+#define PB_LAUNCH_SUB(L, KP_, SW_)                                                                                 \
+  k_gemv_t_sub<T, L, KP_, SW_><<<(unsigned)grid, PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, r, grad, mb, nb, chunk_cols, chunks)
+    if (kp == 1) {
+      PB_LAUNCH_SUB(1, 1, 4);
+    } else if (kp == 2) {
+      PB_LAUNCH_SUB(1, 2, 4);
+    } else {
+      switch (lpc) {
+        case 1: PB_LAUNCH_SUB(1, 4, 1); break;
+        case 2: PB_LAUNCH_SUB(2, 4, 1); break;
+        case 4: PB_LAUNCH_SUB(4, 4, 1); break;
+        case 8: PB_LAUNCH_SUB(8, 4, 1); break;
+        case 16: PB_LAUNCH_SUB(16, 4, 1); break;
+        default: PB_LAUNCH_SUB(32, 4, 1); break;
+      }
     }
 #undef PB_LAUNCH_SUB
     PB_LAUNCH_CHECK(ctx);

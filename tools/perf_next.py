@@ -84,6 +84,10 @@ def main():
     lam = 0.1 * float(tmp.view(ngroups, gsz).norm(dim=1).max())
     del f0, tmp, xt
     torch.cuda.empty_cache()
+    xg, gg = torch.randn(n, device="cuda", generator=gen), torch.empty(n, device="cuda")
+    rec("k4_blockdiag_residual_4x128000", timeit(lambda: L.check(ctx.lib.pb_lsq_blockdiag_residual(ctx.h, L.PB_F32, nblk, mb, nb_, ptr(A), ptr(xg), ptr(b), ptr(f.r))), reps=20), A.numel() * es + n * es)
+    rec("k4_blockdiag_gradient_4x128000", timeit(lambda: L.check(ctx.lib.pb_lsq_blockdiag_gradient(ctx.h, L.PB_F32, nblk, mb, nb_, ptr(A), ptr(f.r), ptr(gg))), reps=20), A.numel() * es + n * es)
+    del xg, gg
     for K, label in ((30, "config3_panoc_lbfgs5_l21"),):
         it = pa.PANOCIteration(torch.zeros(n, device="cuda"), f=f, g=pa.NormL21(lam, gsz))
         st = it.init()
