@@ -22,6 +22,10 @@ struct PbWorkspace {
   double sum_hi[PB_MAX_SUMS][PB_MAX_CTAS];
   double sum_lo[PB_MAX_SUMS][PB_MAX_CTAS];
   double mx[PB_MAX_MAXS][PB_MAX_CTAS];
+  // deferred fold only: snapshot of the scalar block taken by the step kernel (slots other kernels of the iteration wrote, e.g.
+  // the f value in AUX) and the private block the fold kernel completes and exchanges
+  double snap[PB_NSCALARS];
+  double blk[PB_NSCALARS];
 };
 
 struct pb_ctx {
@@ -56,12 +60,21 @@ struct pb_ctx {
   int xchg_fused;                           // K1/K2 push in-kernel
   int xchg_pending;                         // a launched kernel will publish xchg_seq
   int64_t xchg_pending_launch;              // value of `launches` right after that kernel's launch
+  // deferred fold (pipelined driver loop, solve.cu): the fused step only writes its per-CTA partials; a 1-CTA kernel on a
+  // side stream folds them, writes the scalar block and performs the exchange WHILE the next step kernel already runs
+  int defer_fold;                           // 1: pb_fb_step / pb_ffb_step use the split form when the kernel supports it
+  PbWorkspace* ws_defer[2];                 // partial workspaces, alternated by step parity
+  cudaStream_t side_stream;
+  cudaEvent_t ev_main[2], ev_fold[2];
+  unsigned int defer_count;                 // steps issued in deferred form since defer_fold was switched on
+  int last_step_grid;                       // grid size of the most recent k_step launch (the fold kernel needs it)
 };
 
 // Fill the kernel-side parameters for the next in-kernel exchange (advances the sequence number); world = 0 if disabled.
 void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want);
 // Wait for one specific exchange (by sequence number) in the pinned landing zone; rows_out: world x PB_NSCALARS doubles.
 int pb_xchg_wait_seq(pb_ctx* ctx, unsigned int seq, double* rows_out, double timeout_s);
+int pb_step_defer(pb_ctx* ctx, int on);
 
 void pb_set_error(const char* fmt, ...);
 int pb_ensure_scratch(pb_ctx* ctx, size_t bytes);
@@ -206,28 +219,13 @@ __device__ __forceinline__ void block_reduce(Acc<NSUM, NMAX>& a) {
 
 // CTA partial -> workspace; the last CTA to arrive folds all partials in a fixed order (deterministic for a given
 // grid, and -- thanks to the double-double arithmetic -- equal after rounding for any grid) and writes the scalar block.
+// Fold the `nctas` per-CTA partials of `ws` in a fixed order, write the scalar block and (optionally) exchange it.  Executed by
+// ONE CTA: the last CTA of the producing kernel, or the stand-alone fold kernel of the deferred form.
 template <int NSUM, int NMAX, int BLOCK>
-__device__ __forceinline__ void grid_reduce(Acc<NSUM, NMAX>& a, PbWorkspace* ws, double* out, const OutMap& map,
-                                            const XchgParams* xp = nullptr) {
-  __shared__ bool is_last;
-  block_reduce<NSUM, NMAX, BLOCK>(a);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < NSUM; ++k) {
-      ws->sum_hi[k][blockIdx.x] = a.s[k].hi;
-      ws->sum_lo[k][blockIdx.x] = a.s[k].lo;
-    }
-#pragma unroll
-    for (int k = 0; k < NMAX; ++k) ws->mx[k][blockIdx.x] = a.m[k];
-    __threadfence();
-    unsigned int t = atomicAdd(&ws->ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+__device__ __forceinline__ void fold_partials(Acc<NSUM, NMAX>& a, PbWorkspace* ws, unsigned int nctas, double* out,
+                                              const OutMap& map, const XchgParams* xp, bool reset_ticket) {
   a.clear();
-  for (unsigned int c = threadIdx.x; c < gridDim.x; c += BLOCK) {
+  for (unsigned int c = threadIdx.x; c < nctas; c += BLOCK) {
 #pragma unroll
     for (int k = 0; k < NSUM; ++k) {
       dd o;
@@ -249,13 +247,39 @@ __device__ __forceinline__ void grid_reduce(Acc<NSUM, NMAX>& a, PbWorkspace* ws,
 #pragma unroll
     for (int k = 0; k < NMAX; ++k)
       if (map.max_slot[k] >= 0) out[map.max_slot[k]] = a.m[k];
-    ws->ticket = 0;  // ready for the next launch on this stream
+    if (reset_ticket) ws->ticket = 0;  // ready for the next launch on this stream
   }
   // fused C1: the CTA that produced the final scalars also exchanges them with the peers and hands them to the host
   if (xp != nullptr && xp->world > 0) {
     __syncthreads();
     xchg_push_wait(*xp, out);
   }
+}
+
+template <int NSUM, int NMAX, int BLOCK>
+__device__ __forceinline__ void grid_reduce(Acc<NSUM, NMAX>& a, PbWorkspace* ws, double* out, const OutMap& map,
+                                            const XchgParams* xp = nullptr, bool defer = false) {
+  __shared__ bool is_last;
+  block_reduce<NSUM, NMAX, BLOCK>(a);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) {
+      ws->sum_hi[k][blockIdx.x] = a.s[k].hi;
+      ws->sum_lo[k][blockIdx.x] = a.s[k].lo;
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) ws->mx[k][blockIdx.x] = a.m[k];
+    if (!defer) {
+      __threadfence();
+      unsigned int t = atomicAdd(&ws->ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+  }
+  if (defer) return;                    // deferred form: a separate 1-CTA kernel folds (kernel boundary = visibility)
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  fold_partials<NSUM, NMAX, BLOCK>(a, ws, gridDim.x, out, map, xp, true);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -94,6 +94,15 @@ extern "C" int pb_ctx_destroy(pb_ctx* c) {
     if (c->hbuf[k]) cudaFree(c->hbuf[k]);
   if (c->scratch) cudaFree(c->scratch);
   if (c->ws) cudaFree(c->ws);
+  if (c->side_stream) {
+    cudaStreamSynchronize(c->side_stream);
+    for (int k = 0; k < 2; ++k) {
+      if (c->ws_defer[k]) cudaFree(c->ws_defer[k]);
+      if (c->ev_main[k]) cudaEventDestroy(c->ev_main[k]);
+      if (c->ev_fold[k]) cudaEventDestroy(c->ev_fold[k]);
+    }
+    cudaStreamDestroy(c->side_stream);
+  }
   if (c->scalars_own) cudaFree(c->scalars_own);
   if (c->scalars_host) cudaFreeHost(c->scalars_host);
   if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);

@@ -404,6 +404,9 @@ struct Solver {
     int ix = 0, ixn = 1, izp = 0, iz = 1, ig = 0;
     unsigned int seq_k = ctx->xchg_seq;               // published by the init step launched by the caller
     (void)beta_next;
+    // from here on the step kernels leave the fold + exchange to a 1-CTA kernel on the side stream (step_kernels.cu:
+    // launch_step_deferred), so the main stream goes straight from one step kernel to the next
+    if ((rc = pb_step_defer(ctx, 1))) return rc;
     int64_t k = 1;
     for (;;) {
       const bool spec = k < o->maxit;
@@ -411,12 +414,21 @@ struct Solver {
       unsigned int seq_next = 0;
       const int ixf = 3 - ix - ixn, izf = 3 - izp - iz, igo = 1 - ig;
       if (spec) {                                      // fast_forward_backward.jl:130-142 for iteration k+1, launched ahead
-        if ((rc = eval_f_to(X[ixn], G[igo]))) return rc;
+        if ((rc = eval_f_to(X[ixn], G[igo]))) {
+          pb_step_defer(ctx, 0);
+          return rc;
+        }
         const R beta = seq.next(gamma);
-        if ((rc = step_to(X[ixn], G[igo], Z[iz], Z[izf], X[ixf], true, beta))) return rc;
+        if ((rc = step_to(X[ixn], G[igo], Z[iz], Z[izf], X[ixf], true, beta))) {
+          pb_step_defer(ctx, 0);
+          return rc;
+        }
         seq_next = ctx->xchg_seq;
       }
-      if ((rc = read_comb_seq(ctx, seq_k, &sc))) return rc;
+      if ((rc = read_comb_seq(ctx, seq_k, &sc))) {
+        pb_step_defer(ctx, 0);
+        return rc;
+      }
       f_x = f_value(sc);
       g_z = g_value(sc);
       if (k >= o->maxit || stop()) {                   // src/ProximalAlgorithms.jl:117
@@ -433,6 +445,7 @@ struct Solver {
       ++k;
     }
     ctx->xchg_pending = 0;                             // whatever was published last has been consumed or is discarded
+    if ((rc = pb_step_defer(ctx, 0))) return rc;       // main stream waits for the outstanding folds
     x = X[ix];
     x_next = X[ixn];
     z = Z[iz];

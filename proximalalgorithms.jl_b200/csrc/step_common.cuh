@@ -36,6 +36,7 @@ struct StepParams {
   PbWorkspace* ws;
   double* out;
   XchgParams xchg;   // fused per-iteration exchange (world == 0: off)
+  int defer;         // 1: write per-CTA partials only; pb_step_fold_launch folds and exchanges on the side stream
 };
 
 template <typename T, int PROX, bool EXTRAP>

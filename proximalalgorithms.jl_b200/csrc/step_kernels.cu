@@ -4,6 +4,8 @@
 // input array in flight per thread, grid sized as a multiple of the SM count, per-thread double(-double) accumulators,
 // warp-shuffle -> shared -> last-CTA reduction (common.cuh).  All of them are bandwidth bound (1-3 flop/byte), so no
 // tensor-core path exists for this file.
+#include <string.h>
+
 #include "step_common.cuh"
 
 template <typename T, int PROX, bool EXTRAP, int VEC, int UNROLL, bool HINT>
@@ -91,7 +93,27 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
   map.sum_slot[3] = -1;
   map.max_slot[0] = PB_S_RESINF;
   map.max_slot[1] = -1;
-  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map, &p.xchg);
+  // deferred form: freeze the scalar block as the iteration left it (stream order: everything this iteration enqueued before the
+  // step has finished, nothing of the next iteration has started) -- the fold kernel runs concurrently with the next iteration
+  if (p.defer && blockIdx.x == 0 && threadIdx.x < PB_NSCALARS) p.ws->snap[threadIdx.x] = __ldcg(p.out + threadIdx.x);
+  grid_reduce<3, 1, PB_BLOCK>(acc, p.ws, p.out, map, &p.xchg, p.defer != 0);
+}
+
+// Deferred form of the step's epilogue: fold the partials of `nctas` CTAs, write the scalar block, exchange.  <<<1, PB_BLOCK>>>
+// on the context's side stream, overlapping the NEXT step kernel on the main stream.
+__global__ void __launch_bounds__(PB_BLOCK) k_step_fold(PbWorkspace* ws, unsigned int nctas, XchgParams xp) {
+  double* out = ws->blk;
+  if (threadIdx.x < PB_NSCALARS) out[threadIdx.x] = ws->snap[threadIdx.x];
+  __syncthreads();
+  Acc<3, 1> acc;
+  OutMap map;
+  map.sum_slot[0] = PB_S_GSUM;
+  map.sum_slot[1] = PB_S_RESSQ;
+  map.sum_slot[2] = PB_S_GDR;
+  map.sum_slot[3] = -1;
+  map.max_slot[0] = PB_S_RESINF;
+  map.max_slot[1] = -1;
+  fold_partials<3, 1, PB_BLOCK>(acc, ws, nctas, out, map, &xp, false);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -528,15 +550,18 @@ static int launch_step_u(pb_ctx* ctx, const StepParams& p, bool vec_ok, bool hin
     if (hint) {
       auto kern = k_step<T, PROX, EXTRAP, VEC, UNROLL, true>;
       const int grid = resident_grid(ctx, kern, &occ[0], (int64_t)PB_BLOCK * VEC * UNROLL, p.n, 2);
+      ctx->last_step_grid = grid;
       kern<<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
     } else {
       auto kern = k_step<T, PROX, EXTRAP, VEC, UNROLL, false>;
       const int grid = resident_grid(ctx, kern, &occ[1], (int64_t)PB_BLOCK * VEC * UNROLL, p.n, 2);
+      ctx->last_step_grid = grid;
       kern<<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
     }
   } else {
     auto kern = k_step<T, PROX, EXTRAP, 1, UNROLL, false>;
     const int grid = resident_grid(ctx, kern, &occ[2], (int64_t)PB_BLOCK * UNROLL, p.n, 4);
+    ctx->last_step_grid = grid;
     kern<<<grid, PB_BLOCK, 0, ctx->stream>>>(p);
   }
   PB_LAUNCH_CHECK(ctx);
@@ -563,6 +588,39 @@ static int launch_step_t(pb_ctx* ctx, const StepParams& p, bool vec_ok) {
     }
   }
   return launch_step_u<T, PROX, EXTRAP, 4>(ctx, p, vec_ok, hint);
+}
+
+template <typename T, int PROX, bool EXTRAP>
+static int launch_step_t(pb_ctx* ctx, const StepParams& p, bool vec_ok);
+
+// Split form (pb_ctx::defer_fold, set by the pipelined driver loop): the step kernel leaves its per-CTA partials in one of two
+// alternating workspaces; k_step_fold on the side stream folds them, writes the scalar block and does the exchange while the
+// main stream is free to run the next step.  Stream dependencies: fold k waits for step k (event), step k+2 waits for fold k
+// (it reuses the workspace).  The exchange sequence numbers are issued in step order, so the host protocol is unchanged.
+template <typename T, bool EXTRAP>
+static int launch_step_deferred(pb_ctx* ctx, StepParams p, const pb_prox* g, bool vec_ok) {
+  const int par = (int)(ctx->defer_count & 1u);
+  if (ctx->defer_count >= 2) PB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fold[par], 0));
+  p.ws = ctx->ws_defer[par];
+  p.defer = 1;
+  p.xchg.world = 0;
+  int rc;
+  switch (g->kind) {
+    case PB_PROX_ZERO: rc = launch_step_t<T, PB_PROX_ZERO, EXTRAP>(ctx, p, vec_ok); break;
+    case PB_PROX_L1: rc = launch_step_t<T, PB_PROX_L1, EXTRAP>(ctx, p, vec_ok); break;
+    case PB_PROX_BOX: rc = launch_step_t<T, PB_PROX_BOX, EXTRAP>(ctx, p, vec_ok); break;
+    default: rc = launch_step_t<T, PB_PROX_SCALE, EXTRAP>(ctx, p, vec_ok); break;
+  }
+  if (rc != PB_OK) return rc;
+  PB_CHECK_CUDA(cudaEventRecord(ctx->ev_main[par], ctx->stream));
+  PB_CHECK_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_main[par], 0));
+  XchgParams xp;
+  pb_xchg_next(ctx, &xp, true);
+  k_step_fold<<<1, PB_BLOCK, 0, ctx->side_stream>>>(ctx->ws_defer[par], (unsigned int)ctx->last_step_grid, xp);
+  PB_LAUNCH_CHECK(ctx);
+  PB_CHECK_CUDA(cudaEventRecord(ctx->ev_fold[par], ctx->side_stream));
+  ctx->defer_count += 1;
+  return PB_OK;
 }
 
 template <typename T, bool EXTRAP>
@@ -609,6 +667,8 @@ static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool ve
   }
   // measured default: K2 (5 streams) -> register pipeline, K1 (3 streams) -> TMA bulk-copy ring
   const int impl = ctx->step_impl != 0 ? ctx->step_impl : (EXTRAP ? 1 : 2);
+  if (p.defer && impl == 1) return launch_step_deferred<T, EXTRAP>(ctx, p, g, vec_ok);
+  p.defer = 0;
   if (impl == 2 && vec_ok && p.n >= (int64_t)1 << 16) {
     const int rc = pb_launch_step_tma(ctx, sizeof(T) == 4 ? PB_F32 : PB_F64, g->kind, EXTRAP, p);
     if (rc != PB_EUNSUPPORTED) return rc;
@@ -650,12 +710,43 @@ static int step_common(pb_ctx* ctx, int dtype, int64_t n, const void* x, const v
   p.a = p.b = 0.0;
   p.ws = ctx->ws;
   p.out = ctx->scalars_dev;
-  pb_xchg_next(ctx, &p.xchg, ctx->xchg_fused != 0 && n > 0);
+  // deferred fold: only the register-pipeline kernel of the single-pass prox kinds has the split form
+  const int impl_ = ctx->step_impl != 0 ? ctx->step_impl : (extrap ? 1 : 2);
+  p.defer = (ctx->defer_fold && ctx->xchg_fused && n > 0 && impl_ == 1 && g->kind != PB_PROX_L21) ? 1 : 0;
+  if (p.defer)
+    memset(&p.xchg, 0, sizeof(p.xchg));
+  else
+    pb_xchg_next(ctx, &p.xchg, ctx->xchg_fused != 0 && n > 0);
   bool vec_ok = pb_aligned16(x) && pb_aligned16(grad) && pb_aligned16(z) && (!y || pb_aligned16(y)) &&
                 (!res || pb_aligned16(res)) && (!extrap || (pb_aligned16(z_prev) && pb_aligned16(x_next)));
   if (dtype == PB_F32)
     return extrap ? launch_step_prox<float, true>(ctx, p, g, vec_ok) : launch_step_prox<float, false>(ctx, p, g, vec_ok);
   return extrap ? launch_step_prox<double, true>(ctx, p, g, vec_ok) : launch_step_prox<double, false>(ctx, p, g, vec_ok);
+}
+
+// Switch the split (deferred-fold) form of the fused step on / off (internal: used by the pipelined loop of solve.cu).  Turning it
+// off makes the main stream wait for the last fold, so the scalar block and the workspaces are quiescent afterwards.
+int pb_step_defer(pb_ctx* ctx, int on) {
+  if (on) {
+    if (!ctx->side_stream) {
+      PB_CHECK_CUDA(cudaSetDevice(ctx->device));
+      PB_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; ++k) {
+        PB_CHECK_CUDA(cudaMalloc((void**)&ctx->ws_defer[k], sizeof(PbWorkspace)));
+        PB_CHECK_CUDA(cudaMemset(ctx->ws_defer[k], 0, sizeof(PbWorkspace)));
+        PB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_main[k], cudaEventDisableTiming));
+        PB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fold[k], cudaEventDisableTiming));
+      }
+    }
+    ctx->defer_count = 0;
+    ctx->defer_fold = 1;
+    return PB_OK;
+  }
+  if (ctx->defer_fold) {
+    ctx->defer_fold = 0;
+    for (int k = 0; k < 2 && k < (int)ctx->defer_count; ++k) PB_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fold[k], 0));
+  }
+  return PB_OK;
 }
 
 extern "C" int pb_fb_step(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, double gamma,
