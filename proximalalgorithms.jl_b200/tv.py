@@ -107,6 +107,34 @@ class TVSplit:
         return 0.5 * np.sum((u64 - b64) ** 2) + float(self.lam) * (np.abs(np.diff(u64, axis=1)).sum() + np.abs(np.diff(u64, axis=0)).sum())
 
 
+def halo_plan(allinfo, rank, Hglob, es):
+    """Which neighbour rows a shard reads.  `allinfo`: one (rank, row0, H, W, handle_buf0, handle_buf1) per rank.  Returns
+    (prev, next), each None (true image border) or ((handle_buf0, handle_buf1), byte offset of the halo row inside the
+    neighbour's [5][H_nb][W] buffer).  The row above a shard is the LAST row of the upper neighbour, in the copy whose vertical pair
+    (row0 - 1, row0) it is: copy 3 pairs (even, even + 1), copy 4 pairs (odd, odd + 1); symmetrically below."""
+    info = sorted(allinfo, key=lambda r: r[1])
+    W = info[0][3]
+    start = 0
+    for r in info:                                          # shards must tile [0, Hglob) in order
+        if r[1] != start or r[3] != W or r[2] <= 0:
+            raise ValueError("row shards must be non-empty, contiguous, ordered and of equal width")
+        start += r[2]
+    if start != Hglob:
+        raise ValueError("row shards do not cover Hglob rows")
+    pos = [r[0] for r in info].index(rank)
+    _, row0, H, _, _, _ = info[pos]
+    prev = nxt = None
+    if pos > 0:
+        _, _, Hp, _, h0, h1 = info[pos - 1]
+        kc = 3 if (row0 - 1) % 2 == 0 else 4
+        prev = ((h0, h1), (kc * Hp * W + (Hp - 1) * W) * es)
+    if pos + 1 < len(info):
+        _, _, Hn, _, h0, h1 = info[pos + 1]
+        kc = 3 if (row0 + H - 1) % 2 == 0 else 4
+        nxt = ((h0, h1), kc * Hn * W * es)
+    return prev, nxt
+
+
 class TVDouglasRachfordEngine:
     """Buffers and neighbour mappings of the fused TV iteration (used by DouglasRachfordIteration)."""
 
@@ -139,32 +167,17 @@ class TVDouglasRachfordEngine:
         mine = (comm.rank, f.row0, f.H, f.W, self.bufs[0].handle(), self.bufs[1].handle())
         allinfo = [None] * comm.size
         dist.all_gather_object(allinfo, mine, group=getattr(comm, "group", None))
-        allinfo.sort(key=lambda r: r[1])
-        pos = [r[0] for r in allinfo].index(comm.rank)
-        start = 0
-        for r in allinfo:                                   # shards must tile [0, Hglob) in order
-            if r[1] != start or r[3] != f.W:
-                raise ValueError("row shards must be contiguous, ordered and of equal width")
-            start += r[2]
-        if start != f.Hglob:
-            raise ValueError("row shards do not cover Hglob rows")
+        prev, nxt = halo_plan(allinfo, comm.rank, f.Hglob, es)
         prevs, nexts = [None, None], [None, None]
-        if pos > 0:
-            _, _, Hp, _, h0, h1 = allinfo[pos - 1]
-            kc = 3 if (f.row0 - 1) % 2 == 0 else 4          # copy whose vertical pair is (row0 - 1, row0)
-            for i, h in enumerate((h0, h1)):
+        for plan, slots in ((prev, prevs), (nxt, nexts)):
+            if plan is None:
+                continue
+            handles, offset = plan
+            for i, h in enumerate(handles):
                 p = C.c_void_p()
                 L.check(self.ctx.lib.pb_ipc_open(self.ctx.h, h, C.byref(p)))
                 self._opened.append(p)
-                prevs[i] = p.value + (kc * Hp * f.W + (Hp - 1) * f.W) * es
-        if pos + 1 < len(allinfo):
-            _, _, Hn, _, h0, h1 = allinfo[pos + 1]
-            kc = 3 if (f.row0 + f.H - 1) % 2 == 0 else 4    # copy whose vertical pair is (row0 + H - 1, row0 + H)
-            for i, h in enumerate((h0, h1)):
-                p = C.c_void_p()
-                L.check(self.ctx.lib.pb_ipc_open(self.ctx.h, h, C.byref(p)))
-                self._opened.append(p)
-                nexts[i] = p.value + kc * Hn * f.W * es
+                slots[i] = p.value + offset
         self.halo = [(prevs[0], nexts[0]), (prevs[1], nexts[1])]
         torch().cuda.synchronize(self.ctx.device)
         dist.barrier(group=getattr(comm, "group", None))    # every rank's X[0] is filled before anyone reads a halo row

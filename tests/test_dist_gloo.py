@@ -85,3 +85,82 @@ def test_scalar_exchange_world2(n):
         assert gsum == e_g and res_sq == e_r and res_inf == e_i          # exactly rounded, identical on both ranks
         assert abs(gdr - e_d) <= 2 * np.spacing(abs(e_d)) + 1e-25
     assert out[0][1:5] == out[1][1:5]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# N > 1 host path of the row-sharded TV iteration (tv.py): neighbour discovery over the process group and the halo-row
+# addresses handed to the kernel.  The device buffers are stood in by numpy arrays shared through the object all-gather.
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+def _tv_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from proxb200.tv import halo_plan
+
+        H, W = 13, 8
+        bounds = [(0, 5), (5, 13)]
+        rows = bounds[rank]
+        mine = (rank, rows[0], rows[1] - rows[0], W, f"buf0-of-{rank}", f"buf1-of-{rank}")
+        allinfo = [None] * world
+        dist.all_gather_object(allinfo, mine)
+        prev, nxt = halo_plan(allinfo, rank, H, 4)
+        q.put((rank, prev, nxt))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tv_halo_plan_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tv_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict((r, (a, b)) for r, a, b in (q.get(timeout=120) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    W, es = 8, 4
+    # boundary between global rows 4 and 5: row 4 is even -> the pair (4, 5) belongs to copy 3
+    assert out[0][0] is None and out[1][1] is None
+    handles, off = out[0][1]                       # rank 0 reads row 5 = local row 0 of rank 1 (8 rows), copy 3
+    assert handles == ("buf0-of-1", "buf1-of-1") and off == (3 * 8 * W) * es
+    handles, off = out[1][0]                       # rank 1 reads row 4 = last local row of rank 0 (5 rows), copy 3
+    assert handles == ("buf0-of-0", "buf1-of-0") and off == (3 * 5 * W + 4 * W) * es
+
+
+def test_tv_halo_plan_matches_the_oracle_sharding():
+    """The (copy, row) chosen by halo_plan is the one the oracle's sharded prox needs (oracle/tv_oracle.py), for both parities
+    of the boundary, and bad tilings are refused."""
+    from oracle import tv_oracle as tvo
+    from proxb200.tv import halo_plan
+
+    rng = np.random.default_rng(0)
+    H, W = 11, 6
+    b = rng.standard_normal((H, W)).astype(np.float32)
+    X = rng.standard_normal((5, H, W)).astype(np.float32)
+    full, _ = tvo.TVSplit(b, np.float32(0.3), (H, W)).prox(X.reshape(-1), np.float32(0.9))
+    full = full.reshape(5, H, W)
+    for split in (4, 5, 6):
+        info = [(0, 0, split, W, "a0", "a1"), (1, split, H - split, W, "b0", "b1")]
+        top, bot = np.ascontiguousarray(X[:, :split]), np.ascontiguousarray(X[:, split:])
+        (_, off_next) = halo_plan(info, 0, H, 4)[1]
+        (_, off_prev) = halo_plan(info, 1, H, 4)[0]
+        halo_next = bot.reshape(-1)[off_next // 4: off_next // 4 + W]
+        halo_prev = top.reshape(-1)[off_prev // 4: off_prev // 4 + W]
+        ft = tvo.TVSplit(b[:split], np.float32(0.3), (split, W), 0, H)
+        fb = tvo.TVSplit(b[split:], np.float32(0.3), (H - split, W), split, H)
+        ft.halo_next, fb.halo_prev = halo_next, halo_prev
+        yt, _ = ft.prox(top.reshape(-1), np.float32(0.9))
+        yb, _ = fb.prox(bot.reshape(-1), np.float32(0.9))
+        assert np.array_equal(yt.reshape(5, split, W), full[:, :split]) and np.array_equal(yb.reshape(5, H - split, W), full[:, split:])
+    with pytest.raises(ValueError):
+        halo_plan([(0, 0, 4, W, "a", "a"), (1, 5, 6, W, "b", "b")], 0, H, 4)        # gap
+    with pytest.raises(ValueError):
+        halo_plan([(0, 0, 4, W, "a", "a"), (1, 4, 6, W, "b", "b")], 0, H, 4)        # does not cover H

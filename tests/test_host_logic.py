@@ -114,3 +114,56 @@ def test_iteration_parameter_defaults_follow_reference():
     assert alg.maxit == 7 and alg.kwargs == {"Lf": 2.0} and alg.iterator_type is pa.FastForwardBackwardIteration
     with pytest.raises(TypeError):
         pa.ForwardBackwardIteration(x0=np.zeros(3, np.int32))
+
+
+def test_tv_engine_connect_glue(monkeypatch):
+    """TVDouglasRachfordEngine._connect (tv.py) end to end with stand-ins for the process group and the cudaIpc calls: the
+    neighbour's two ping-pong buffers are opened and the halo addresses are base + offset of halo_plan."""
+    import ctypes as C
+    import types
+
+    from proxb200 import tv
+
+    W, es = 8, 4
+    infos = [(0, 0, 5, W, b"h00", b"h01"), (1, 5, 8, W, b"h10", b"h11")]
+    bases = {b"h00": 0x1000000, b"h01": 0x2000000, b"h10": 0x3000000, b"h11": 0x4000000}
+    opened, closed, barriers = [], [], []
+
+    class FakeLib:
+        def pb_ipc_open(self, h, handle, pp):
+            opened.append(handle)
+            pp._obj.value = bases[handle]
+            return 0
+
+        def pb_ipc_close(self, h, p):
+            closed.append(p.value)
+            return 0
+
+    class FakeDist:
+        def all_gather_object(self, out, mine, group=None):
+            assert mine[:4] == infos[1][:4]
+            out[:] = infos
+
+        def barrier(self, group=None):
+            barriers.append(1)
+
+    class FakeBuf:
+        def __init__(self, h):
+            self.h = h
+
+        def handle(self):
+            return self.h
+
+    monkeypatch.setattr(tv, "torch", lambda: types.SimpleNamespace(cuda=types.SimpleNamespace(synchronize=lambda dev: None)))
+    eng = object.__new__(tv.TVDouglasRachfordEngine)
+    eng.f = types.SimpleNamespace(comm=types.SimpleNamespace(dist=FakeDist(), rank=1, size=2), R=np.float32, H=8, W=W, row0=5, Hglob=13)
+    eng.ctx = types.SimpleNamespace(lib=FakeLib(), h=C.c_void_p(1), device="cuda:1")
+    eng.bufs = [FakeBuf(b"h10"), FakeBuf(b"h11")]
+    eng._opened = []
+    eng._connect()
+    assert opened == [b"h00", b"h01"] and barriers == [1]
+    off = (3 * 5 * W + 4 * W) * es                      # last row of rank 0's copy 3 (the pair (4, 5) is an even pair)
+    assert eng.halo == [(0x1000000 + off, None), (0x2000000 + off, None)]
+    eng.bufs = None
+    eng.close()
+    assert closed == [0x1000000, 0x2000000]
