@@ -223,4 +223,95 @@ end
 ProximalAlgorithms.default_stopping_criterion(tol, ::FastForwardBackwardIteration, st::B200FFBState) = st.res_inf / st.gamma <= tol
 ProximalAlgorithms.default_solution(::FastForwardBackwardIteration, st::B200FFBState) = st.z
 
+# ======================================================================================================================
+# "Next" rows (SURVEY.md section 8f): L-BFGS operator and Douglas-Rachford on B200Vector.  Same status as the rest of this file:
+# unexecuted here; the Python hosts accel.py / douglas_rachford.py issue exactly these calls and are tested on B200.
+# ======================================================================================================================
+const S_AUX2, S_AUX3 = 13, 15                              # <s,y>, <y,y> of pb_lbfgs_update (1-based hi words)
+const PB_PROX_SQRL2 = Cint(5)
+
+pair(s::Vector{Float64}, i::Int) = s[i] + s[i + 1]          # a double-double sum of the scalar block, rounded once
+
+# ---- LBFGSOperator{M} on device vectors: src/accel/lbfgs.jl:5-28 (storage), :102-104 (initialize) ---------------------
+mutable struct B200LBFGSOperator{R,T}
+    h::Ptr{Cvoid}
+    ctx::B200Context
+end
+
+function ProximalAlgorithms.initialize(::ProximalAlgorithms.LBFGS{M}, x::B200Vector{T}) where {M,T}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pb_lbfgs_create, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Cint, Ref{Ptr{Cvoid}}), x.ctx.h, pbdtype(T), length(x), M, h))
+    op = B200LBFGSOperator{real(T),T}(h[], x.ctx)
+    finalizer(o -> ccall((:pb_lbfgs_destroy, LIB), Cint, (Ptr{Cvoid},), o.h), op)
+    return op
+end
+
+ProximalAlgorithms.acceleration_style(::Type{<:B200LBFGSOperator}) = ProximalAlgorithms.QuasiNewtonStyle()
+
+# reset!, lbfgs.jl:53-56
+ProximalAlgorithms.reset!(L::B200LBFGSOperator) = (check(ccall((:pb_lbfgs_reset, LIB), Cint, (Ptr{Cvoid},), L.h)); L)
+
+# update!(L, s, y), lbfgs.jl:30-51: one fused pass (ring slot + <s,y> + <y,y>), one scalar read-back, host-side `if ys > 0`
+function ProximalAlgorithms.update!(L::B200LBFGSOperator, s::B200Vector, y::B200Vector)
+    check(ccall((:pb_lbfgs_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                L.ctx.h, L.h, s.ptr, C_NULL, y.ptr, C_NULL))
+    sc = read_scalars!(L.ctx)
+    acc = Ref{Cint}(0)
+    check(ccall((:pb_lbfgs_commit, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ref{Cint}), L.h, pair(sc, S_AUX2), pair(sc, S_AUX3), acc))
+    return L
+end
+
+# mul!(d, L, v), lbfgs.jl:66-95: the two-loop recursion as 2*currmem + 2 launches with device-resident coefficients
+function LinearAlgebra.mul!(d::B200Vector{T}, L::B200LBFGSOperator, v::B200Vector{T}) where {T}
+    check(ccall((:pb_lbfgs_apply, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                L.ctx.h, L.h, v.ptr, 1.0, d.ptr, C_NULL, C_NULL))
+    return d
+end
+Base.:*(L::B200LBFGSOperator, v::B200Vector) = mul!(similar(v), L, v)
+
+# PANOC's fused form (panoc.jl:114-117 + :183): d = -(H * res) and x_d = x + d in the last launch of the chain
+function panoc_direction!(d::B200Vector{T}, x_d::B200Vector{T}, L::B200LBFGSOperator, res::B200Vector{T}, x::B200Vector{T}) where {T}
+    check(ccall((:pb_lbfgs_apply, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                L.ctx.h, L.h, res.ptr, -1.0, d.ptr, x.ptr, x_d.ptr))
+    return d
+end
+
+# `tau .* x_d .+ (1 - tau) .* z_curr` and friends (panoc.jl:214-215, :234-237), products and sum rounded separately
+function lincomb2!(out::B200Vector{T}, a, x::B200Vector{T}, b, y::B200Vector{T}) where {T}
+    check(ccall((:pb_lincomb2, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}),
+                out.ctx.h, pbdtype(T), length(out), Float64(a), x.ptr, Float64(b), y.ptr, out.ptr))
+    return out
+end
+
+# ---- DouglasRachford for element-wise f, g: src/algorithms/douglas_rachford.jl:54-63 as ONE kernel per iteration ----------
+mutable struct B200DRState{R,T}
+    x::B200Vector{T}            # current x
+    x_in::B200Vector{T}         # x before the last update (y, r, z, res are recomputed from it on demand)
+    res_inf::R
+end
+
+function dr_pass!(iter, st::B200DRState{R,T}, y, r, z, res) where {R,T}
+    ctx = st.x.ctx
+    fd, gd = Ref(descriptor(iter.f, T)), Ref(descriptor(iter.g, T))
+    check(ccall((:pb_dr_step, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cdouble, Ref{PbProx}, Ref{PbProx}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                ctx.h, pbdtype(T), length(st.x), st.x_in.ptr, Float64(iter.gamma), fd, gd, st.x.ptr, y, r, z, res))
+    st.res_inf = R(read_scalars!(ctx)[S_RESINF])
+end
+
+function Base.iterate(iter::ProximalAlgorithms.DouglasRachfordIteration{R,C,<:B200Vector{T}},
+                      st::B200DRState{R,T} = B200DRState{R,T}(copy(iter.x0), similar(iter.x0), zero(R))) where {R,C,T}
+    st.x_in, st.x = st.x, st.x_in
+    dr_pass!(iter, st, C_NULL, C_NULL, C_NULL, C_NULL)
+    return st, st
+end
+
+ProximalAlgorithms.default_stopping_criterion(tol, iter::ProximalAlgorithms.DouglasRachfordIteration, st::B200DRState) =
+    st.res_inf / iter.gamma <= tol
+function ProximalAlgorithms.default_solution(iter::ProximalAlgorithms.DouglasRachfordIteration, st::B200DRState{R,T}) where {R,T}
+    y = similar(st.x)                                        # state.y = prox_f(x_in): re-run the pass with y requested
+    dr_pass!(iter, st, y.ptr, C_NULL, C_NULL, C_NULL)
+    return y
+end
+
 end # module
