@@ -8,8 +8,6 @@ from __future__ import annotations
 
 import ctypes as C
 
-import numpy as np
-
 from . import _lib as L
 from .host import Context, LocalComm, check_vec, pb_dtype, ptr, real_type, torch
 
@@ -135,4 +133,3 @@ def acceleration_style(directions):
 
 
 __all__ = ["LBFGS", "LBFGSOperator", "NoAcceleration", "acceleration_style", "QuasiNewtonStyle", "NoAccelerationStyle"]
-_ = np  # numpy is part of the public typing of R

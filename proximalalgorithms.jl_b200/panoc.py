@@ -25,7 +25,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib as L
-from .accel import LBFGS, NoAccelerationStyle, QuasiNewtonStyle, acceleration_style
+from .accel import LBFGS, QuasiNewtonStyle, acceleration_style
 from .algorithms import IterativeAlgorithm, _Engine, _resolve, _to_device_copy, f_model
 from .functions import Deferred, MatrixOp, Zero
 from .host import pb_dtype, ptr, real_type, torch
@@ -206,7 +206,7 @@ class PANOCIteration:
 
     # ---- step, panoc.jl:138-255 ---------------------------------------------------------------------------------------
     def step(self, st):
-        R, e, t = self.R, st._engine, torch()
+        R, e = self.R, st._engine
         dt, n = pb_dtype(R), st.x.numel()
         ident = self.A is None
         inf = R(np.inf)
@@ -319,7 +319,6 @@ class PANOCIteration:
                 st.H.enqueue_update(st.x, st.x_prev, st.res, st.res_prev)
                 sc = e.read()[1]
             st.H.commit(sc)
-        _ = t
         return st
 
     def __iter__(self):
@@ -355,5 +354,3 @@ def PANOC(maxit=1_000, tol=1e-8, stop=None, solution=default_solution, verbose=F
             return default_stopping_criterion(_tol, it, state)
     return IterativeAlgorithm(PANOCIteration, maxit, stop, solution, verbose, freq, display, driver="python", **kwargs)
 
-
-_ = NoAccelerationStyle
