@@ -119,6 +119,15 @@ class _Engine:
             L.check(lib.pb_extrapolate(ctx.h, dt, n, ptr(z), ptr(z_prev), float(beta), ptr(x_next)))
         return lambda sc_: R(g_z)
 
+    def pre_resolve(self, R, g, fx):
+        """A Deferred f value lives in the AUX slot until the iteration's read-back.  The two-phase (IndBallL2) and user-prox
+        forms of the step run `pb_forward` first, which reuses that slot for ||y||^2: fetch the value before they do.  Fused
+        prox kinds never touch AUX, so for them this is a no-op (no extra synchronisation)."""
+        if getattr(g, "fused", False) or not isinstance(fx, Deferred):
+            return fx
+        row, sc = self.read()
+        return _resolve(fx, R, row, sc)
+
     def read(self):
         """The one host synchronisation of an iteration: returns (this rank's raw row, rank-combined Scalars)."""
         sc = self.comm.exchange(self.ctx)
@@ -258,6 +267,7 @@ class ForwardBackwardIteration:
     def init(self):
         st = ForwardBackwardState()
         e, fx = self._init_state(st)
+        fx = e.pre_resolve(self.R, self.g, fx)
         g_of = e.fb_step(self.R, self.g, st.x, st.grad_f_x, st.gamma, st.z, y_scratch=st._y_scratch)   # :71-72, :82
         st.grad_f_z = torch().empty_like(st.x)                                                          # :62
         self._finish(st, fx, g_of)
@@ -308,7 +318,7 @@ class ForwardBackwardIteration:
             fx = st.f_x
         else:                                                                               # :111-115
             st.x, st.z = st.z, st.x
-            fx = e.eval_f(self.f, st.x, st.grad_f_x)
+            fx = e.pre_resolve(R, self.g, e.eval_f(self.f, st.x, st.grad_f_x))
         g_of = e.fb_step(R, self.g, st.x, st.grad_f_x, st.gamma, st.z, y_scratch=st._y_scratch)       # :117-120
         self._finish(st, fx, g_of)
         return st
@@ -339,6 +349,7 @@ class FastForwardBackwardIteration(ForwardBackwardIteration):
     def init(self):
         st = FastForwardBackwardState()
         e, fx = self._init_state(st)                                                        # :74-78
+        fx = e.pre_resolve(self.R, self.g, fx)
         t = torch()
         st.z_prev = st.x.clone()                                                            # :69 default z_prev = copy(x)
         if self.extrapolation_sequence is not None:                                         # :90-94
@@ -368,14 +379,14 @@ class FastForwardBackwardIteration(ForwardBackwardIteration):
             st.beta = beta
             L.check(e.lib.pb_extrapolate(e.ctx.h, dt, n, ptr(st.z), ptr(st.z_prev), float(beta), ptr(st.x)))   # :135
             st.z_prev, st.z = st.z, st.z_prev                                               # :136
-            fx = e.eval_f(self.f, st.x, st.grad_f_x)                                        # :138-139
+            fx = e.pre_resolve(R, self.g, e.eval_f(self.f, st.x, st.grad_f_x))              # :138-139
             g_of = e.fb_step(R, self.g, st.x, st.grad_f_x, st.gamma, st.z, y_scratch=st._y_scratch)    # :140-142
         else:
             st.gamma = R(self.gamma)                                                        # :130-132
             st.beta = st._beta_next
             st.x, st._x_next = st._x_next, st.x                                             # :135 (computed by the previous pass)
             st.z_prev, st.z = st.z, st.z_prev                                               # :136
-            fx = e.eval_f(self.f, st.x, st.grad_f_x)                                        # :138-139
+            fx = e.pre_resolve(R, self.g, e.eval_f(self.f, st.x, st.grad_f_x))              # :138-139
             st._beta_next = self._next_beta(st)
             g_of = e.fb_step(R, self.g, st.x, st.grad_f_x, st.gamma, st.z, z_prev=st.z_prev, beta=st._beta_next,
                              x_next=st._x_next, y_scratch=st._y_scratch)                    # :140-142 (+ next :135)

@@ -148,6 +148,7 @@ class PANOCIteration:
         st.At_grad_f_Ax = st.grad_f_Ax if ident else self.A.mul_t_into(new_n(), st.grad_f_Ax)   # :96
         st.z, st.res = new_n(), new_n()
         st._y_scratch = None if getattr(self.g, "fused", False) else new_n()
+        fx = e.pre_resolve(R, self.g, fx)
         g_of = self._step_kernel(st)                                                        # :97-98, :109
         self._read(st, fx, g_of)
         st.H = self.directions.initialize(st.x) if self.style is QuasiNewtonStyle else None   # :110
@@ -256,6 +257,7 @@ class PANOCIteration:
         nr = R(np.sqrt(np.float64(res_sq_x)))
         threshold = np.float64(FBE_x) - sigma * np.float64(R(nr * nr)) + np.float64(tol)
 
+        fxd = e.pre_resolve(R, self.g, fxd)
         g_of = self._step_kernel(st)                                                        # :199-201
         if st.H is not None:                                                                # speculative :252 (tau = 1 accepted)
             st.H.enqueue_update(st.x, st.x_prev, st.res, st.res_prev)
@@ -307,7 +309,7 @@ class PANOCIteration:
                     self._lincomb(e, st.tau, st.grad_f_Ax_d, one_m, st.grad_f_Az, st.grad_f_Ax)
                 self._lincomb(e, st.tau, st.At_grad_f_Ax_d, one_m, st.At_grad_f_Az, st.At_grad_f_Ax)
             else:                                                                           # :238-244
-                fx = e.eval_f(self.f, st.Ax, st.grad_f_Ax)
+                fx = e.pre_resolve(R, self.g, e.eval_f(self.f, st.Ax, st.grad_f_Ax))
                 if not ident:
                     self.A.mul_t_into(st.At_grad_f_Ax, st.grad_f_Ax)
             g_of = self._step_kernel(st)                                                    # :246-248

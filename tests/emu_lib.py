@@ -27,11 +27,11 @@ def _addr(p):
 
 def _vec(p, n, dt):
     a = _addr(p)
-    if a == 0:
-        return None
     T = np.float32 if dt == L.PB_F32 else np.float64
     if n == 0:
-        return np.zeros(0, T)
+        return np.zeros(0, T)            # empty tensors have a null data pointer
+    if a == 0:
+        return None
     ct = C.c_float if T is np.float32 else C.c_double
     return np.ctypeslib.as_array((ct * int(n)).from_address(a))
 

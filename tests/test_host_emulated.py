@@ -260,3 +260,36 @@ def test_afba_host_logic_matches_oracle(emu, golden, T):
         pa.AFBAIteration(np.zeros(5, T), np.zeros(5, T), f=pa.LeastSquares(A, b))
     with pytest.raises(ValueError):
         pa.AFBAIteration(np.zeros(5, T), np.zeros(5, T), lambda_=0.5)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_two_phase_and_user_prox_keep_the_smooth_value(emu, golden, T):
+    """IndBallL2 (two-phase prox) and user `prox_` callbacks run `pb_forward` inside the step, which reuses the scalar slot that
+    carries a built-in f's value: the engine must fetch f first (`_Engine.pre_resolve`).  Adaptive stepsizes and PANOC's
+    line search consume that value, so a wrong f shows up as a different iteration count."""
+    d = golden("lasso_small")
+    A, b = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T)
+    n = A.shape[1]
+    tol = T(1e-6 if T is np.float64 else 1e-4)
+    x, it = pa.PANOC(tol=tol)(x0=np.zeros(n, T), f=pa.LeastSquares(A, b), g=pa.IndBallL2(0.5))
+    xo, ito = po.panoc(np.zeros(n, T), f=o.LeastSquares(A, b), g=o.IndBallL2(T(0.5)), tol=tol)
+    assert abs(it - ito) <= max(3, ito // 10) and np.max(np.abs(x - xo)) <= (1e-9 if T is np.float64 else 1e-3)
+    for mk, mko in ((pa.FastForwardBackward, o.fast_forward_backward), (pa.ForwardBackward, o.forward_backward)):
+        z, it = mk(tol=tol, driver="python")(x0=np.zeros(n, T), f=pa.LeastSquares(A, b), g=pa.IndBallL2(0.5))
+        zo, ito = mko(np.zeros(n, T), o.LeastSquares(A, b), o.IndBallL2(T(0.5)), tol=tol)
+        assert abs(it - ito) <= max(2, ito // 50) and np.max(np.abs(z - zo)) <= (1e-9 if T is np.float64 else 1e-3), (mk.__name__, it, ito)
+
+    class UserL1:
+        def prox_(self, z, y, gam):
+            zz, v = o.NormL1(T(1)).prox(y.numpy(), gam)
+            z.copy_(torch.as_tensor(zz))
+            return v
+
+    z, it = pa.FastForwardBackward(tol=tol)(x0=np.zeros(n, T), f=pa.LeastSquares(A, b), g=UserL1())
+    zo, ito = o.fast_forward_backward(np.zeros(n, T), o.LeastSquares(A, b), o.NormL1(T(1)), tol=tol)
+    assert abs(it - ito) <= max(2, ito // 50) and np.max(np.abs(z - zo)) <= (1e-9 if T is np.float64 else 1e-3)
+
+
+def test_empty_iterates(emu):
+    assert pa.DouglasRachford(maxit=3)(x0=np.zeros(0), f=pa.NormL1(1.0), g=pa.IndBox(-1, 1), gamma=1.0)[1] == 1
+    assert pa.PANOC(maxit=3)(x0=np.zeros(0), g=pa.NormL1(1.0), gamma=1.0)[1] == 1
