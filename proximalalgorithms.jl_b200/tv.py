@@ -197,11 +197,18 @@ class TVDouglasRachfordEngine:
             self.cur = dst
         return self.X[dst]
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def close(self):
-        for p in self._opened:
+        """Unmap the neighbours' buffers and free this rank's (sharded runs only; idempotent)."""
+        for p in getattr(self, "_opened", []):
             self.ctx.lib.pb_ipc_close(self.ctx.h, p)
         self._opened = []
-        if self.bufs:
+        if getattr(self, "bufs", None):
             torch().cuda.synchronize(self.ctx.device)
             for b_ in self.bufs:
                 b_.free()
