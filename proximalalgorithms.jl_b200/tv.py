@@ -197,14 +197,9 @@ class TVDouglasRachfordEngine:
             self.cur = dst
         return self.X[dst]
 
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
     def close(self):
-        """Unmap the neighbours' buffers and free this rank's (sharded runs only; idempotent)."""
+        """Unmap the neighbours' buffers and free this rank's (sharded runs only; idempotent).  Explicit on purpose: `state.x` is
+        a tensor view of these buffers, so they must outlive every reference a caller may still hold."""
         for p in getattr(self, "_opened", []):
             self.ctx.lib.pb_ipc_close(self.ctx.h, p)
         self._opened = []
