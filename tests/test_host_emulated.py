@@ -293,3 +293,19 @@ def test_two_phase_and_user_prox_keep_the_smooth_value(emu, golden, T):
 def test_empty_iterates(emu):
     assert pa.DouglasRachford(maxit=3)(x0=np.zeros(0), f=pa.NormL1(1.0), g=pa.IndBox(-1, 1), gamma=1.0)[1] == 1
     assert pa.PANOC(maxit=3)(x0=np.zeros(0), g=pa.NormL1(1.0), gamma=1.0)[1] == 1
+
+
+def test_afba_linear_program_host_logic(emu, golden):
+    """test/problems/test_linear_programs.jl:102-125 through the product's host logic (IndNonnegative = IndBox(0, inf), IndPoint(b) =
+    IndBox(b, b) with per-element bounds, f = LinearFunction(c)): the four optimality measures of the reference's assert_lp_solution."""
+    d = golden("unit_linear_program")
+    A, b, c = d["A"], d["b"], d["c"]
+    tol = 100 * np.finfo(np.float64).eps
+    bt = torch.as_tensor(b.copy())
+    (x, y), it = pa.AFBA(tol=tol, maxit=100_000)(x0=np.zeros(10), y0=np.zeros(8), f=pa.LinearFunction(torch.as_tensor(c.copy())),
+                                                  g=pa.IndBox(0.0, float("inf")), h=pa.IndBox(bt, bt), L=A, beta_f=0)
+    (xo, yo), ito = ao.afba(np.zeros(10), np.zeros(8), f=ao.LinearSmooth(c), g=o.IndBox(0.0, np.inf), h=o.IndBox(b, b), L=A, beta_f=0, tol=tol, maxit=100_000)
+    assert abs(it - ito) <= max(5, ito // 20), (it, ito)
+    x64, y64 = x.astype(np.float64), y.astype(np.float64)
+    quality = (-min(0.0, x64.min()), np.linalg.norm(A @ x64 - b), max(0.0, (-A.T @ y64 - c).max()), abs((c + A.T @ y64) @ x64))
+    assert all(q <= 1000 * tol for q in quality), quality
