@@ -243,6 +243,12 @@ int pb_ipc_export(pb_ctx* ctx, void* dptr, void* handle_out);
 int pb_ipc_open(pb_ctx* ctx, const void* handle, void** dptr);
 int pb_ipc_close(pb_ctx* ctx, void* dptr);
 
+/* ---- K11: forward differences of an H x W row-major image and the adjoint (anisotropic TV by Chambolle-Pock: the `L` of
+ * src/algorithms/primal_dual.jl with h = lambda*||.||_1).  forward: out[0][i][j] = u[i][j+1] - u[i][j] (0 in the last column),
+ * out[1][i][j] = u[i+1][j] - u[i][j] (0 in the last row); adjoint: the exact transpose.  out must not alias the input. */
+int pb_fd2d_forward(pb_ctx* ctx, int dtype, int64_t H, int64_t W, const void* u, void* out /* 2*H*W */);
+int pb_fd2d_adjoint(pb_ctx* ctx, int dtype, int64_t H, int64_t W, const void* pq /* 2*H*W */, void* out /* H*W */);
+
 /* ---- K9: prox of the dense least-squares term (DouglasRachford's `f = LeastSquares(A, b)`, test_lasso_small.jl:39,205-214;
  * benchmark/benchmarks.jl:87-93).  ProximalOperators' LeastSquaresDirect restated: q = lambda*A'b + x/gamma; tall A:
  * y = (lambda*A'A + I/gamma)^-1 q; wide A: y = gamma*(q - lambda*A'((lambda*AA' + I/gamma)^-1 (A q))).  A (column-major m x n,

@@ -116,6 +116,8 @@ SIGNATURES = {
     "pb_ipc_export": (_i, [_vp, _vp, _vp]),
     "pb_ipc_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "pb_ipc_close": (_i, [_vp, _vp]),
+    "pb_fd2d_forward": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
+    "pb_fd2d_adjoint": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
     "pb_lsq_prox_create": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _d, C.POINTER(_vp)]),
     "pb_lsq_prox_destroy": (_i, [_vp]),
     "pb_lsq_prox_apply": (_i, [_vp, _vp, _vp, _d, _vp]),
