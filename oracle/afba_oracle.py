@@ -8,7 +8,8 @@ display), :334-427 (default stepsizes).  `l` is restricted to the default IndZer
 Prox of a convex conjugate follows ProximalCore's Moreau identity (third party, restated):
     prox_{gamma h*}(v) = v - gamma * prox_{h/gamma}(v/gamma)
 Pinned (tests/test_oracle_afba.py) against x_star and the iteration bounds of test/problems/test_lasso_small.jl:233-275 (three
-formulations) and test/problems/test_elasticnet.jl:56-113 (five (theta, mu) pairs).
+formulations), test/problems/test_elasticnet.jl:56-113 (five (theta, mu) pairs) and the linear program of
+test/problems/test_linear_programs.jl:44-151 (AFBA and VuCondat to 1000 * 100 eps in all four optimality measures).
 """
 from __future__ import annotations
 
@@ -98,6 +99,16 @@ class SqrNormL2Smooth:
     def value_and_gradient(self, x):
         R = _R(x)
         return R(R(self.lam) / R(2) * np.sum(x * x, dtype=R)), (R(self.lam) * x).astype(x.dtype)
+
+
+class LinearSmooth:
+    """f(x) = <c, x> (test/problems/test_linear_programs.jl:104: AutoDifferentiable(x -> dot(c, x)))."""
+
+    def __init__(self, c):
+        self.c = c
+
+    def value_and_gradient(self, x):
+        return _R(x)(self.c @ x), self.c.copy()
 
 
 class AFBAIteration:

@@ -726,17 +726,43 @@ static int step_common(pb_ctx* ctx, int dtype, int64_t n, const void* x, const v
 
 // Switch the split (deferred-fold) form of the fused step on / off (internal: used by the pipelined loop of solve.cu).  Turning it
 // off makes the main stream wait for the last fold, so the scalar block and the workspaces are quiescent afterwards.
+// Side stream, the two alternating workspaces and the chaining events of the split form; all or nothing.
+static int defer_setup(pb_ctx* ctx) {
+  cudaStream_t side = nullptr;
+  PbWorkspace* ws[2] = {nullptr, nullptr};
+  cudaEvent_t em[2] = {nullptr, nullptr}, ef[2] = {nullptr, nullptr};
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    e = cudaMalloc((void**)&ws[k], sizeof(PbWorkspace));
+    if (e == cudaSuccess) e = cudaMemset(ws[k], 0, sizeof(PbWorkspace));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&em[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ef[k], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    for (int k = 0; k < 2; ++k) {
+      if (ws[k]) cudaFree(ws[k]);
+      if (em[k]) cudaEventDestroy(em[k]);
+      if (ef[k]) cudaEventDestroy(ef[k]);
+    }
+    if (side) cudaStreamDestroy(side);
+    pb_set_error("pb_step_defer: %s", cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? PB_ENOMEM : PB_ECUDA;
+  }
+  for (int k = 0; k < 2; ++k) {
+    ctx->ws_defer[k] = ws[k];
+    ctx->ev_main[k] = em[k];
+    ctx->ev_fold[k] = ef[k];
+  }
+  ctx->side_stream = side;
+  return PB_OK;
+}
+
 int pb_step_defer(pb_ctx* ctx, int on) {
   if (on) {
     if (!ctx->side_stream) {
-      PB_CHECK_CUDA(cudaSetDevice(ctx->device));
-      PB_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-      for (int k = 0; k < 2; ++k) {
-        PB_CHECK_CUDA(cudaMalloc((void**)&ctx->ws_defer[k], sizeof(PbWorkspace)));
-        PB_CHECK_CUDA(cudaMemset(ctx->ws_defer[k], 0, sizeof(PbWorkspace)));
-        PB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_main[k], cudaEventDisableTiming));
-        PB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fold[k], cudaEventDisableTiming));
-      }
+      const int rc = defer_setup(ctx);
+      if (rc != PB_OK) return rc;
     }
     ctx->defer_count = 0;
     ctx->defer_fold = 1;

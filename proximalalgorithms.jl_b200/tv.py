@@ -198,10 +198,12 @@ class TVDouglasRachfordEngine:
         return self.X[dst]
 
     def close(self):
-        for p in self._opened:
+        """Unmap the neighbours' buffers and free this rank's (sharded runs only; idempotent).  Explicit on purpose: `state.x` is
+        a tensor view of these buffers, so they must outlive every reference a caller may still hold."""
+        for p in getattr(self, "_opened", []):
             self.ctx.lib.pb_ipc_close(self.ctx.h, p)
         self._opened = []
-        if self.bufs:
+        if getattr(self, "bufs", None):
             torch().cuda.synchronize(self.ctx.device)
             for b_ in self.bufs:
                 b_.free()

@@ -15,6 +15,7 @@ Sources (all paths relative to /root/reference):
   * test/accel/test_lbfgs.jl:6-101 -- literal Q, q, xs and the five reference L-BFGS directions.
   * test/problems/test_sparse_logistic_small.jl:34 -- literal x_star.
   * test/problems/test_elasticnet.jl:27 -- literal x_star.
+  * test/problems/test_linear_programs.jl:44-96 -- literal LP data (x_star, s_star, y_star, A).
 The literals are parsed out of the .jl files with regular expressions (nothing is copied by hand).
 """
 import hashlib
@@ -136,6 +137,17 @@ def unit_elasticnet():
     return dict(xstar=xs)
 
 
+def unit_linear_program():
+    """test/problems/test_linear_programs.jl:44-96: literal x_star, s_star, y_star, A (8 x 10); b = A x*, c = A' y* + s*."""
+    src = open(os.path.join(REF, "test", "problems", "test_linear_programs.jl")).read()
+    xs = _vector(_block_after(src, "x_star = T["))
+    ss = _vector(_block_after(src, "s_star = T["))
+    ys = _vector(_block_after(src, "y_star = T["))
+    a = _matrix(_block_after(src, "A = T["))
+    assert xs.shape == (10,) and ss.shape == (10,) and ys.shape == (8,) and a.shape == (8, 10)
+    return dict(A=np.asfortranarray(a), xstar=xs, sstar=ss, ystar=ys, b=a @ xs, c=a.T @ ys + ss)
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not present: golden fixtures can only be regenerated in the build container")
@@ -149,6 +161,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "lbfgs_known_answers.npz"), **lbfgs_known_answers())
     np.savez_compressed(os.path.join(OUT, "unit_sparse_logistic.npz"), **unit_sparse_logistic())
     np.savez_compressed(os.path.join(OUT, "unit_elasticnet.npz"), **unit_elasticnet())
+    np.savez_compressed(os.path.join(OUT, "unit_linear_program.npz"), **unit_linear_program())
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 

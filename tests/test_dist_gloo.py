@@ -164,3 +164,92 @@ def test_tv_halo_plan_matches_the_oracle_sharding():
         halo_plan([(0, 0, 4, W, "a", "a"), (1, 5, 6, W, "b", "b")], 0, H, 4)        # gap
     with pytest.raises(ValueError):
         halo_plan([(0, 0, 4, W, "a", "a"), (1, 4, 6, W, "b", "b")], 0, H, 4)        # does not cover H
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# N > 1 host path of a whole sharded solve: two gloo ranks, each running the product's FastForwardBackward / ForwardBackward host
+# logic on its row shard with the kernels replaced by the numpy ABI emulation (tests/emu_lib.py), exchange = TorchDistComm.
+# Adaptive stepsize: the Lipschitz estimate needs n_global, the line search needs f summed over the shards.
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+def _emulated_solver_setup():
+    import proxb200 as pa
+    from proxb200 import accel, algorithms, functions, host
+
+    from emu_lib import EmuContext
+
+    ctx = EmuContext()
+    ctx.scal = torch.from_numpy(ctx.lib.scal)            # TorchDistComm all-gathers the context's scalar-block tensor
+    host.Context.get = classmethod(lambda cls, device=None: ctx)
+
+    def check_vec(t_, n=None, dtype=None):
+        assert t_.dim() == 1
+
+    for mod in (host, functions, algorithms, accel):
+        mod.check_vec = check_vec
+    return pa, ctx
+
+
+def _problem(n=600):
+    rng = np.random.default_rng(42)
+    b = rng.standard_normal(n) * (rng.random(n) < 0.3) * 3.0
+    return b, 0.7
+
+
+def _solve_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pa, ctx = _emulated_solver_setup()
+        from proxb200.host import TorchDistComm, shard_bounds
+
+        b, lam = _problem()
+        lo, hi = shard_bounds(b.size, world)[rank]
+        comm = TorchDistComm()
+        out = {}
+        for name, mk in (("ffb", pa.FastForwardBackward), ("fb", pa.ForwardBackward)):
+            z, it = mk(tol=1e-9, maxit=500, driver="python")(x0=np.full(hi - lo, 2.0), f=pa.SquaredDistance(b[lo:hi]), g=pa.NormL1(lam),
+                                                           comm=comm, n_global=b.size)
+            out[name] = (it, z)
+        q.put((rank, out))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_solve_world2_matches_unsharded_host_logic():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_solve_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # the same problem unsharded, in a fresh interpreter state of this process's emulation
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from proxb200 import accel, algorithms, functions, host
+
+    saved = (host.Context.__dict__["get"], [(m, m.check_vec) for m in (host, functions, algorithms, accel)])
+    try:
+        pa, _ = _emulated_solver_setup()
+        b, lam = _problem()
+        for name, mk in (("ffb", pa.FastForwardBackward), ("fb", pa.ForwardBackward)):
+            z1, it1 = mk(tol=1e-9, maxit=500, driver="python")(x0=np.full(b.size, 2.0), f=pa.SquaredDistance(b), g=pa.NormL1(lam))
+            z2 = np.concatenate([res[r][name][1] for r in range(world)])
+            assert res[0][name][0] == res[1][name][0] == it1 and it1 < 500          # same iteration count on both ranks and unsharded
+            assert np.array_equal(z2, z1)                                           # and the same bits
+            want = np.sign(b) * np.maximum(np.abs(b) - lam, 0)                      # closed form: soft threshold
+            assert np.max(np.abs(z1 - want)) <= 1e-8
+    finally:
+        host.Context.get = saved[0]
+        for m, f in saved[1]:
+            m.check_vec = f

@@ -349,25 +349,3 @@ def test_pipelined_native_loop_is_invisible(T):
         s1, s2 = a1.last_state, a2.last_state
         assert torch.equal(s1.x, s2.x) and torch.equal(s1.z_prev, s2.z_prev) and torch.equal(s1.grad_f_x, s2.grad_f_x)
         assert s1.f_x == s2.f_x and s1.g_z == s2.g_z and float(s1.res_norm_inf) == float(s2.res_norm_inf)
-
-
-@pytest.mark.parametrize("T", TYPES)
-def test_two_phase_prox_with_adaptive_stepsize_and_panoc(T):
-    """IndBallL2's two-phase step runs `pb_forward`, which reuses the AUX slot carrying a built-in f's value; the engine fetches f
-    first (`_Engine.pre_resolve`).  The adaptive line searches and PANOC consume that value (host-logic twin of this test:
-    tests/test_host_emulated.py::test_two_phase_and_user_prox_keep_the_smooth_value)."""
-    from oracle import panoc_oracle as po
-
-    d = load_golden("lasso_small")
-    A, b = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T)
-    n = A.shape[1]
-    tol = T(1e-6 if T == np.float64 else 1e-4)
-    close = 1e-6 if T == np.float64 else 2e-3
-    for mk, mko in ((pa.FastForwardBackward, o.fast_forward_backward), (pa.ForwardBackward, o.forward_backward)):
-        z, it = mk(tol=tol)(x0=np.zeros(n, T), f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)))
-        zo, ito = mko(np.zeros(n, T), o.LeastSquares(A, b), o.IndBallL2(T(0.5)), tol=tol)
-        assert abs(it - ito) <= max(5, ito // 20), (mk.__name__, it, ito)
-        assert np.max(np.abs(z - zo)) <= close
-    x, it = pa.PANOC(tol=tol)(x0=np.zeros(n, T), f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)))
-    xo, ito = po.panoc(np.zeros(n, T), f=o.LeastSquares(A, b), g=o.IndBallL2(T(0.5)), tol=tol)
-    assert it <= 2 * ito + 5 and np.max(np.abs(x - xo)) <= 10 * close, (it, ito)

@@ -327,3 +327,67 @@ def test_chambolle_pock_tv_with_the_stencil_operator(emu):
     u = st.z[: H * W]
     assert it < 20000 and np.max(np.abs(x - u)) <= 1e-5
     assert abs(f.objective(x) - f.objective(u)) <= 1e-8 * f.objective(u)
+
+
+def test_afba_linear_program_host_logic(emu, golden):
+    """test/problems/test_linear_programs.jl:102-125 through the product's host logic (IndNonnegative = IndBox(0, inf), IndPoint(b) =
+    IndBox(b, b) with per-element bounds, f = LinearFunction(c)): the four optimality measures of the reference's assert_lp_solution."""
+    d = golden("unit_linear_program")
+    A, b, c = d["A"], d["b"], d["c"]
+    tol = 100 * np.finfo(np.float64).eps
+    bt = torch.as_tensor(b.copy())
+    (x, y), it = pa.AFBA(tol=tol, maxit=100_000)(x0=np.zeros(10), y0=np.zeros(8), f=pa.LinearFunction(torch.as_tensor(c.copy())),
+                                                  g=pa.IndBox(0.0, float("inf")), h=pa.IndBox(bt, bt), L=A, beta_f=0)
+    (xo, yo), ito = ao.afba(np.zeros(10), np.zeros(8), f=ao.LinearSmooth(c), g=o.IndBox(0.0, np.inf), h=o.IndBox(b, b), L=A, beta_f=0, tol=tol, maxit=100_000)
+    assert abs(it - ito) <= max(5, ito // 20), (it, ito)
+    x64, y64 = x.astype(np.float64), y.astype(np.float64)
+    quality = (-min(0.0, x64.min()), np.linalg.norm(A @ x64 - b), max(0.0, (-A.T @ y64 - c).max()), abs((c + A.T @ y64) @ x64))
+    assert all(q <= 1000 * tol for q in quality), quality
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_panoc_reference_problems_with_user_callbacks(emu, golden, T):
+    """The reference's remaining PANOC tests through the product's host logic, with the smooth term supplied the way the reference
+    supplies it (a user callback, i.e. NOT a built-in quadratic): test_sparse_logistic_small.jl:101-109 (adaptive, A a matrix),
+    test_lasso_small_strongly_convex.jl:155-162, test_nonconvex_qp.jl:68-103 (random 100-dim box-constrained QPs)."""
+    A, b, _, _ = _lasso_4x5(golden, T)
+
+    class Logistic:                                     # logistic_loss(u - b), labels all one
+        def value_and_gradient(self, u):
+            v, g = po.LogisticLoss(b).value_and_gradient(u.numpy())
+            return v, torch.as_tensor(g)
+
+    d = golden("unit_sparse_logistic")
+    x, it = pa.PANOC(adaptive=True, tol=T(1e-6))(x0=np.zeros(5, T), f=Logistic(), A=A, g=pa.NormL1(float(d["lam"])))
+    assert x.dtype == T and np.max(np.abs(x - d["xstar"].astype(T))) <= 1e-4 and it < 50
+
+    sc = golden("unit_lasso_sc_5x5")
+    A2, b2, x02 = np.asfortranarray(sc["A"].astype(T)), sc["b"].astype(T), sc["x0"].astype(T)
+
+    class LsqCallback:                                  # fA_autodiff of the reference test
+        def value_and_gradient(self, x):
+            v, g = o.LeastSquares(A2, b2).value_and_gradient(x.numpy())
+            return v, torch.as_tensor(g)
+
+    y, it = pa.PANOC(tol=T(1e-4))(x0=x02, f=LsqCallback(), g=pa.NormL1(T(sc["lam"])), Lf=T(sc["Lf"]))
+    assert np.max(np.abs(y - sc["xstar"].astype(T))) <= 1e-4 and it < 45 and np.array_equal(x02, sc["x0"].astype(T))
+
+    if T is np.float64:
+        for k in range(1, 4):
+            rng = np.random.default_rng(k)
+            n = 100
+            U, _ = np.linalg.qr(rng.standard_normal((n, n)))
+            ev = 2 * rng.random(n) - 1
+            Q = U @ np.diag(ev) @ U.T
+            Q = 0.5 * (Q + Q.T)
+            qv = rng.standard_normal(n)
+
+            class QP:
+                def value_and_gradient(self, x):
+                    v, g = po.QuadraticForm(Q, qv).value_and_gradient(x.numpy())
+                    return v, torch.as_tensor(g)
+
+            gamma = 0.95 / np.max(np.abs(ev))
+            x, it = pa.PANOC(tol=1e-4)(x0=np.zeros(n), f=QP(), g=pa.IndBox(-1.0, 1.0))
+            z = np.minimum(1.0, np.maximum(-1.0, x - gamma * (Q @ x + qv)))
+            assert np.max(np.abs(x - z)) / gamma <= 1e-4 and it < 1000

@@ -57,3 +57,22 @@ def test_afba_argument_errors_and_aliases(golden):
     assert np.max(np.abs(x - xstar)) <= 1e-4
     (x, y), it = ao.vu_condat(np.zeros(5), np.zeros(5), f=o.LeastSquares(A, b), g=o.NormL1(lam), beta_f=np.linalg.norm(A, 2) ** 2, tol=1e-7)
     assert np.max(np.abs(x - xstar)) <= 1e-4
+
+
+def _lp_quality(d, x, y):
+    A, b, c = d["A"], d["b"], d["c"]
+    x, y = x.astype(np.float64), y.astype(np.float64)
+    return (-min(0.0, x.min()), np.linalg.norm(A @ x - b), max(0.0, (-A.T @ y - c).max()), abs((c + A.T @ y) @ x))
+
+
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("solver", ["afba", "vu_condat"])
+def test_linear_program_like_the_reference(golden, T, solver):
+    # test/problems/test_linear_programs.jl:102-151: f = <c, .>, g = IndNonnegative, h = IndPoint(b), L = A, beta_f = 0
+    d = golden("unit_linear_program")
+    A, b, c = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T), d["c"].astype(T)
+    tol, maxit = 100 * np.finfo(T).eps, 100_000
+    x0, y0 = np.zeros(10, T), np.zeros(8, T)
+    (x, y), it = getattr(ao, solver)(x0, y0, f=ao.LinearSmooth(c), g=o.IndBox(T(0), T(np.inf)), h=o.IndBox(b, b), L=A, beta_f=0, tol=tol, maxit=maxit)
+    assert x.dtype == T and y.dtype == T and it <= maxit and not x0.any() and not y0.any()
+    assert all(q <= 1000 * tol for q in _lp_quality(d, x, y)), _lp_quality(d, x, y)
