@@ -317,6 +317,30 @@ typedef struct pb_solve_result {
 int pb_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* opts, void* x,
              void* grad, void* z, void* z_prev, void* x_next, void* grad_z, void* scratch, pb_solve_result* result);
 
+/* ---- native PANOC driver (src/algorithms/panoc.jl:88-259 around the kernels above; twin of the Python host panoc.py) -------
+ * f is a built-in smooth term acting on A x (A = NULL: the identity; else dense column-major Am x n), g a single-pass prox kind,
+ * directions L-BFGS with memory lbfgs_mem (0: NoAcceleration).  Work vectors are allocated and released by the call; the solution
+ * state.z is copied to z_out.  Single GPU. */
+typedef struct pb_panoc_opts {
+  int64_t maxit;
+  double tol;              /* stop when norm(res, Inf)/gamma <= tol (negative: never)                                */
+  double alpha, beta;      /* panoc.jl:45-46 (0.95, 0.5)                                                           */
+  double gamma;            /* stepsize; <= 0: alpha / lower_bound_smoothness_constant (requires adaptive)          */
+  double minimum_gamma;
+  int32_t adaptive, max_backtracks, lbfgs_mem, quadratic;   /* quadratic: ProximalCore.is_generalized_quadratic(f)  */
+  int64_t Am, An;
+  const void* A;
+} pb_panoc_opts;
+
+typedef struct pb_panoc_result {
+  int64_t iterations, gamma_backtracks, tau_backtracks;
+  double gamma, f_Ax, g_z, res_inf, tau;
+  int32_t warned_small_gamma, pad;
+} pb_panoc_result;
+
+int pb_panoc_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_panoc_opts* opts,
+                   const void* x0, void* z_out, pb_panoc_result* result);
+
 /* ---- host-buffer convenience (the "plugin call with HOST buffers"): upload x, grad, z_prev, run K2, download z, x_next
  * and the scalar block.  All host pointers; temporary device buffers are cached in the context. */
 int pb_ffb_step_host(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev,
