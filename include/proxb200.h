@@ -243,6 +243,12 @@ int pb_ipc_export(pb_ctx* ctx, void* dptr, void* handle_out);
 int pb_ipc_open(pb_ctx* ctx, const void* handle, void** dptr);
 int pb_ipc_close(pb_ctx* ctx, void* dptr);
 
+/* ---- K11: forward differences of an H x W row-major image and the adjoint (anisotropic TV by Chambolle-Pock: the `L` of
+ * src/algorithms/primal_dual.jl with h = lambda*||.||_1).  forward: out[0][i][j] = u[i][j+1] - u[i][j] (0 in the last column),
+ * out[1][i][j] = u[i+1][j] - u[i][j] (0 in the last row); adjoint: the exact transpose.  out must not alias the input. */
+int pb_fd2d_forward(pb_ctx* ctx, int dtype, int64_t H, int64_t W, const void* u, void* out /* 2*H*W */);
+int pb_fd2d_adjoint(pb_ctx* ctx, int dtype, int64_t H, int64_t W, const void* pq /* 2*H*W */, void* out /* H*W */);
+
 /* ---- K9: prox of the dense least-squares term (DouglasRachford's `f = LeastSquares(A, b)`, test_lasso_small.jl:39,205-214;
  * benchmark/benchmarks.jl:87-93).  ProximalOperators' LeastSquaresDirect restated: q = lambda*A'b + x/gamma; tall A:
  * y = (lambda*A'A + I/gamma)^-1 q; wide A: y = gamma*(q - lambda*A'((lambda*AA' + I/gamma)^-1 (A q))).  A (column-major m x n,
@@ -310,6 +316,30 @@ typedef struct pb_solve_result {
 /* x holds copy(x0) on entry.  grad, z, scratch: n-vectors.  z_prev, x_next: FFB only.  grad_z: adaptive FB only. */
 int pb_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* opts, void* x,
              void* grad, void* z, void* z_prev, void* x_next, void* grad_z, void* scratch, pb_solve_result* result);
+
+/* ---- native PANOC driver (src/algorithms/panoc.jl:88-259 around the kernels above; twin of the Python host panoc.py) -------
+ * f is a built-in smooth term acting on A x (A = NULL: the identity; else dense column-major Am x n), g a single-pass prox kind,
+ * directions L-BFGS with memory lbfgs_mem (0: NoAcceleration).  Work vectors are allocated and released by the call; the solution
+ * state.z is copied to z_out.  Single GPU. */
+typedef struct pb_panoc_opts {
+  int64_t maxit;
+  double tol;              /* stop when norm(res, Inf)/gamma <= tol (negative: never)                                */
+  double alpha, beta;      /* panoc.jl:45-46 (0.95, 0.5)                                                           */
+  double gamma;            /* stepsize; <= 0: alpha / lower_bound_smoothness_constant (requires adaptive)          */
+  double minimum_gamma;
+  int32_t adaptive, max_backtracks, lbfgs_mem, quadratic;   /* quadratic: ProximalCore.is_generalized_quadratic(f)  */
+  int64_t Am, An;
+  const void* A;
+} pb_panoc_opts;
+
+typedef struct pb_panoc_result {
+  int64_t iterations, gamma_backtracks, tau_backtracks;
+  double gamma, f_Ax, g_z, res_inf, tau;
+  int32_t warned_small_gamma, pad;
+} pb_panoc_result;
+
+int pb_panoc_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_panoc_opts* opts,
+                   const void* x0, void* z_out, pb_panoc_result* result);
 
 /* ---- host-buffer convenience (the "plugin call with HOST buffers"): upload x, grad, z_prev, run K2, download z, x_next
  * and the scalar block.  All host pointers; temporary device buffers are cached in the context. */

@@ -52,6 +52,18 @@ class pb_solve_result(C.Structure):
                 ("step_kernel_launches", C.c_int64)]
 
 
+class pb_panoc_opts(C.Structure):
+    _fields_ = [("maxit", C.c_int64), ("tol", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double),
+                ("minimum_gamma", C.c_double), ("adaptive", C.c_int32), ("max_backtracks", C.c_int32), ("lbfgs_mem", C.c_int32),
+                ("quadratic", C.c_int32), ("Am", C.c_int64), ("An", C.c_int64), ("A", C.c_void_p)]
+
+
+class pb_panoc_result(C.Structure):
+    _fields_ = [("iterations", C.c_int64), ("gamma_backtracks", C.c_int64), ("tau_backtracks", C.c_int64), ("gamma", C.c_double),
+                ("f_Ax", C.c_double), ("g_z", C.c_double), ("res_inf", C.c_double), ("tau", C.c_double), ("warned_small_gamma", C.c_int32),
+                ("pad", C.c_int32)]
+
+
 PB_F_LSQ_DENSE, PB_F_LSQ_BLOCKDIAG, PB_F_SQDIST, PB_F_LINEAR = 0, 1, 2, 3
 PB_ALG_FB, PB_ALG_FFB = 0, 1
 PB_SEQ_ADAPTIVE, PB_SEQ_FIXED, PB_SEQ_SIMPLE, PB_SEQ_CONSTANT = 0, 1, 2, 3
@@ -116,12 +128,15 @@ SIGNATURES = {
     "pb_ipc_export": (_i, [_vp, _vp, _vp]),
     "pb_ipc_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "pb_ipc_close": (_i, [_vp, _vp]),
+    "pb_fd2d_forward": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
+    "pb_fd2d_adjoint": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
     "pb_lsq_prox_create": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _d, C.POINTER(_vp)]),
     "pb_lsq_prox_destroy": (_i, [_vp]),
     "pb_lsq_prox_apply": (_i, [_vp, _vp, _vp, _d, _vp]),
     "pb_dr_step": (_i, [_vp, _i, _i64, _vp, _d, _pp, _pp, _vp, _vp, _vp, _vp, _vp]),
     "pb_solve": (_i, [_vp, _i, _i64, C.POINTER(pb_smooth), _pp, C.POINTER(pb_solve_opts), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                       C.POINTER(pb_solve_result)]),
+    "pb_panoc_solve": (_i, [_vp, _i, _i64, C.POINTER(pb_smooth), _pp, C.POINTER(pb_panoc_opts), _vp, _vp, C.POINTER(pb_panoc_result)]),
     "pb_ffb_step_host": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _d, _d, _pp, _vp, _vp, C.POINTER(C.c_double)]),
 }
 

@@ -20,6 +20,7 @@ from .accel import LBFGS, LBFGSOperator, NoAcceleration  # noqa: F401
 from .douglas_rachford import DouglasRachford, DouglasRachfordIteration, DouglasRachfordState  # noqa: F401
 from .functions import (  # noqa: F401
     BlockDiagLeastSquares,
+    FiniteDifference2D,
     IndBallL2,
     IndBox,
     LeastSquares,

@@ -106,6 +106,36 @@ class MatrixOp:
         return out
 
 
+class FiniteDifference2D:
+    """Forward differences of an H x W row-major image, L u = (D_x u, D_y u) in R^{2HW} (zero in the last column / row), and
+    the exact adjoint: the linear map of anisotropic total variation lambda*||L u||_1 for the primal-dual methods
+    (`ChambollePock(g=SqrNormL2(1, b), h=NormL1(lam), L=FiniteDifference2D(H, W))`)."""
+
+    def __init__(self, H, W, device=None):
+        self.ctx = Context.get(device)
+        self.H, self.W = int(H), int(W)
+        self.n, self.m = self.H * self.W, 2 * self.H * self.W
+
+    def _dt(self, x):
+        return pb_dtype(real_type(x.dtype))
+
+    def mul_into(self, out, x):
+        check_vec(x, self.n)
+        check_vec(out, self.m, x.dtype)
+        L.check(self.ctx.lib.pb_fd2d_forward(self.ctx.h, self._dt(x), self.H, self.W, ptr(x), ptr(out)))
+        return out
+
+    def mul_t_into(self, out, v):
+        check_vec(v, self.m)
+        check_vec(out, self.n, v.dtype)
+        L.check(self.ctx.lib.pb_fd2d_adjoint(self.ctx.h, self._dt(v), self.H, self.W, ptr(v), ptr(out)))
+        return out
+
+    def opnorm(self):
+        """Upper bound sqrt(8) of ||L|| (attained in the limit of large images); the default primal-dual stepsizes only need a bound."""
+        return float(np.sqrt(8.0))
+
+
 class LeastSquares:
     """f(x) = 0.5*||A x - b||^2 for a dense matrix, with the benchmark's explicit gradient
     `res = A*x - b; (norm(res)^2/2, A'*res)` (benchmark/benchmarks.jl:11-17).

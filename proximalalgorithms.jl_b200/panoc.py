@@ -349,10 +349,79 @@ def default_display(k, it, state):
         print("%5d | %.3e | %.3e | %.3e" % (k, float(state.gamma), float(state.res_norm_inf / state.gamma), float(state.tau)))
 
 
-def PANOC(maxit=1_000, tol=1e-8, stop=None, solution=default_solution, verbose=False, freq=10, display=default_display, **kwargs):
+def _native_panoc(alg, it, tol):
+    """Run the whole solve in `pb_panoc_solve` (csrc/panoc_solve.cu) if every ingredient is built in; returns (z, k) or None."""
+    import ctypes as C
+    import warnings
+
+    from .accel import LBFGS as _LBFGS
+    from .accel import NoAcceleration as _NoAcc
+    from .algorithms import _like_input
+
+    f, g, R = it.f, it.g, it.R
+    if not hasattr(f, "native_descriptor") or not getattr(g, "fused", False):
+        return None
+    if g.kind not in (L.PB_PROX_ZERO, L.PB_PROX_L1, L.PB_PROX_BOX, L.PB_PROX_L21):
+        return None
+    if it.A is not None and not isinstance(it.A, MatrixOp):
+        return None
+    if not isinstance(it.directions, (_LBFGS, _NoAcc)) or (it.gamma is None and not it.adaptive):
+        return None
+    fdesc = f.native_descriptor()
+    if fdesc is None:
+        return None
+    e = _Engine(it, it.x0)
+    if e.comm.size != 1:
+        return None
+    t = torch()
+    x0 = _to_device_copy(it.x0, e.ctx)
+    z = t.empty_like(x0)
+    n = x0.numel()
+    A = it.A
+    opts = L.pb_panoc_opts(alg.maxit, float(tol), float(it.alpha), float(it.beta), 0.0 if it.gamma is None else float(R(it.gamma)),
+                           float(it.minimum_gamma), 1 if it.adaptive else 0, it.max_backtracks,
+                           it.directions.M if isinstance(it.directions, _LBFGS) else 0, 1 if _is_quadratic(f) else 0,
+                           A.m if A is not None else 0, A.n if A is not None else 0, A.A_cm.data_ptr() if A is not None else None)
+    gdesc = g.descriptor(R)
+    res = L.pb_panoc_result()
+    L.check(e.lib.pb_panoc_solve(e.ctx.h, pb_dtype(R), n, C.byref(fdesc), C.byref(gdesc), C.byref(opts), ptr(x0), ptr(z), C.byref(res)))
+    if res.warned_small_gamma:
+        warnings.warn(f"stepsize `gamma` became too small ({R(res.gamma)})")
+    it.backtracks, it.tau_backtracks = int(res.gamma_backtracks), int(res.tau_backtracks)
+    alg.last_native = res
+    return _like_input(it.x0, z), int(res.iterations)
+
+
+class _PanocAlgorithm(IterativeAlgorithm):
+    """driver="native": the loop runs inside the library (pb_panoc_solve) when all ingredients are built in; "python" (default while
+    the native twin awaits its first hardware run) keeps the loop in this file."""
+
+    def __call__(self, **kwargs):
+        if self.driver == "native":
+            it = self.iterator_type(**{**self.kwargs, **kwargs})
+            tol = getattr(self.stop, "_default_tol", None)
+            out = None
+            if tol is not None and self.solution is default_solution and not self.verbose:
+                out = _native_panoc(self, it, tol)
+            if out is None:
+                raise L.ProxB200Error("driver='native' requested but this PANOC problem needs the Python loop")
+            self.last_driver = "native"
+            self.last_iteration = it
+            return out
+        self.last_driver = "python"
+        saved, self.driver = self.driver, "python"
+        try:
+            return super().__call__(**kwargs)
+        finally:
+            self.driver = saved
+
+
+def PANOC(maxit=1_000, tol=1e-8, stop=None, solution=default_solution, verbose=False, freq=10, display=default_display,
+          driver="python", **kwargs):
     """panoc.jl:296-315."""
     if stop is None:
         def stop(it, state, _tol=tol):
             return default_stopping_criterion(_tol, it, state)
-    return IterativeAlgorithm(PANOCIteration, maxit, stop, solution, verbose, freq, display, driver="python", **kwargs)
+        stop._default_tol = tol
+    return _PanocAlgorithm(PANOCIteration, maxit, stop, solution, verbose, freq, display, driver=driver, **kwargs)
 

@@ -423,6 +423,26 @@ def _tv_step(self, h, dt, H, W, x, b, gamma, lam, x_out, y, z, row0, Hglob, hp, 
 EmuLib.pb_dr_tv_step = _tv_step
 
 
+def _fd_forward(self, h, dt, H, W, u, out):
+    from oracle.stencil_oracle import FiniteDifference2D
+
+    self.launches += 1
+    _vec(out, 2 * H * W, dt)[...] = FiniteDifference2D(H, W).mul(_vec(u, H * W, dt).copy())
+    return 0
+
+
+def _fd_adjoint(self, h, dt, H, W, pq, out):
+    from oracle.stencil_oracle import FiniteDifference2D
+
+    self.launches += 1
+    _vec(out, H * W, dt)[...] = FiniteDifference2D(H, W).mul_t(_vec(pq, 2 * H * W, dt).copy())
+    return 0
+
+
+EmuLib.pb_fd2d_forward = _fd_forward
+EmuLib.pb_fd2d_adjoint = _fd_adjoint
+
+
 class EmuContext:
     """Stands in for host.Context: CPU tensors, EmuLib, memcpy-style read-back."""
 

@@ -68,3 +68,33 @@ def test_linear_program_like_the_reference(T, solver):
     quality = (-min(0.0, x64.min()), np.linalg.norm(A64 @ x64 - b64), max(0.0, (-A64.T @ y64 - c64).max()), abs((c64 + A64.T @ y64) @ x64))
     assert all(q <= 1000 * tol for q in quality), quality
     assert it <= 3 * ito + 100, (it, ito)          # same convergence regime as the oracle (the reference only asserts it <= maxit)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_native_panoc_driver_equals_python_host(T):
+    """pb_panoc_solve (csrc/panoc_solve.cu) is a native twin of panoc.py: same kernels, same scalar arithmetic in R -> identical
+    iteration counts, backtrack counters and bit-identical solutions."""
+    d = load_golden("lasso_small")
+    A, b, lam = np.asfortranarray(d["A"].astype(T)), d["b"].astype(T), T(d["lam"])
+    n = A.shape[1]
+    Lf = T(np.linalg.norm(d["A"], 2) ** 2)
+    tol = T(1e-6 if T == np.float64 else 1e-4)
+    cases = [
+        dict(f=lambda: pa.LeastSquares(A, b), A=None, kw={}),                                   # adaptive, A = I, quadratic branch
+        dict(f=lambda: pa.LeastSquares(A, b), A=None, kw=dict(Lf=Lf)),                          # fixed stepsize
+        dict(f=lambda: pa.SquaredDistance(b), A=A, kw={}),                                      # matrix A, general branch
+        dict(f=lambda: pa.SquaredDistance(b), A=A, kw=dict(Lf=Lf, directions=pa.NoAcceleration())),
+        dict(f=lambda: pa.LeastSquares(A, b), A=None, kw=dict(directions=pa.LBFGS(2), max_backtracks=3)),
+    ]
+    for case in cases:
+        for g in (pa.NormL1(lam), pa.IndBox(T(-0.05), T(0.05)), pa.NormL21(lam, 4)):
+            kw = dict(case["kw"])
+            if case["A"] is not None:
+                kw["A"] = case["A"]
+            sp, sn = pa.PANOC(tol=tol, maxit=400), pa.PANOC(tol=tol, maxit=400, driver="native")
+            zp, itp = sp(x0=np.zeros(n, T), f=case["f"](), g=g, **kw)
+            zn, itn = sn(x0=np.zeros(n, T), f=case["f"](), g=g, **kw)
+            assert sn.last_driver == "native" and itn == itp, (itn, itp, type(g).__name__, list(kw))
+            assert np.array_equal(zn, zp)
+            assert sn.last_iteration.tau_backtracks == sp.last_iteration.tau_backtracks
+            assert sn.last_iteration.backtracks == sp.last_iteration.backtracks

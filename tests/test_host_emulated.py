@@ -295,6 +295,40 @@ def test_empty_iterates(emu):
     assert pa.PANOC(maxit=3)(x0=np.zeros(0), g=pa.NormL1(1.0), gamma=1.0)[1] == 1
 
 
+def test_chambolle_pock_tv_with_the_stencil_operator(emu):
+    """Row f4 as SURVEY.md describes it: TV denoising by Chambolle-Pock with L = forward differences, h = lam*||.||_1.  Host logic
+    against the AFBA oracle run on the dense matrix of the same operator; the minimiser agrees with the Douglas-Rachford TV
+    splitting (oracle/tv_oracle.py)."""
+    from oracle.stencil_oracle import FiniteDifference2D as FDo
+
+    T = np.float64
+    rng = np.random.default_rng(4)
+    H, W = 6, 7
+    img = np.zeros((H, W))
+    img[2:5, 1:4] = 1.0
+    b = (img + 0.1 * rng.standard_normal((H, W))).reshape(-1)
+    lam = 0.2
+    Ld = np.stack([FDo(H, W).mul(e) for e in np.eye(H * W)], axis=1)                  # dense 2HW x HW matrix of L
+    v = rng.standard_normal(2 * H * W)
+    assert np.allclose(Ld.T @ v, FDo(H, W).mul_t(v), atol=1e-14)                     # mul_t is the exact transpose
+    gam = (0.3, 0.3)                                                                   # gamma1*gamma2*||L||^2 = 0.72 < 1
+    it_o = ao.AFBAIteration(np.zeros(H * W), np.zeros(2 * H * W), g=po.SqrNormL2Translated(b, 1.0), h=o.NormL1(lam), L=Ld, theta=2, gamma=gam)
+    it_p = pa.AFBAIteration(np.zeros(H * W), np.zeros(2 * H * W), g=pa.SqrNormL2(1.0, b), h=pa.NormL1(lam), L=pa.FiniteDifference2D(H, W), theta=2, gamma=gam)
+    for k, (so, sp) in enumerate(zip(it_o, it_p)):
+        assert np.max(np.abs(sp.xbar.numpy() - so.xbar)) <= 1e-12 and np.max(np.abs(sp.ybar.numpy() - so.ybar)) <= 1e-12, k
+        if k == 15:
+            break
+    (x, y), it = pa.ChambollePock(tol=1e-9, maxit=20000)(x0=np.zeros(H * W), y0=np.zeros(2 * H * W), g=pa.SqrNormL2(1.0, b), h=pa.NormL1(lam),
+                                                        L=pa.FiniteDifference2D(H, W))
+    f = tvo.TVSplit(b.reshape(H, W), lam, (H, W))
+    dr = iter(po.DouglasRachfordIteration(np.tile(b, 5), f=f, g=tvo.Consensus(5), gamma=1.0))
+    for _ in range(6000):
+        st = next(dr)
+    u = st.z[: H * W]
+    assert it < 20000 and np.max(np.abs(x - u)) <= 1e-5
+    assert abs(f.objective(x) - f.objective(u)) <= 1e-8 * f.objective(u)
+
+
 def test_afba_linear_program_host_logic(emu, golden):
     """test/problems/test_linear_programs.jl:102-125 through the product's host logic (IndNonnegative = IndBox(0, inf), IndPoint(b) =
     IndBox(b, b) with per-element bounds, f = LinearFunction(c)): the four optimality measures of the reference's assert_lp_solution."""
