@@ -55,6 +55,9 @@ def parse():
                    help="per-iteration scalar exchange: device = in-kernel NVLink push + pinned-flag poll (default); "
                         "nccl = all_gather + D2H copy; memcpy = cudaMemcpy read-back (N=1 only)")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    p.add_argument("--cpu-threads", type=int, default=0,
+                   help="OpenMP threads of the CPU port (0 = all host cores this process may use; set explicitly because "
+                        "torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)")
     return p.parse_args()
 
 
@@ -66,12 +69,24 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any (profiles/traffic.json)."""
+def ncu_traffic(n_per_gpu):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch at `n` elements).  The kernel streams every element once, so
+    a launch on n_per_gpu elements moves n_per_gpu / n of the captured bytes; null when there is no capture."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_step_ffb_l1_f32"]["dram_bytes_per_launch_at_n"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_step_ffb_l1_f32"]
+        return float(t["dram_bytes_per_launch_at_n"]) * (n_per_gpu / float(t["n"]))
     except Exception:
         return None
+
+
+def host_threads(args):
+    if args.cpu_threads > 0:
+        return args.cpu_threads
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -128,11 +143,13 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU baseline: the C port of the oracle (unfused passes, all host threads)
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_port_run(n, steps, warmup, seconds_budget=None):
+def cpu_port_run(n, steps, warmup, seconds_budget=None, threads=0):
     """Time `steps` unfused FISTA iterations of the port on n elements (after `warmup`).  If seconds_budget is given the
     step count is reduced to fit it (at least 2).  Returns (seconds_per_step, steps_done, threads)."""
     from oracle import fb_port
 
+    if threads > 0:
+        fb_port.set_threads(threads)
     T = np.float32
     z, zp, grad = (np.empty(n, T) for _ in range(3))
     fb_port.fill(z, 3)
@@ -163,10 +180,11 @@ def run_reference(args):
         return
     n = args.n
     # bound the run: probe one step on the full size, shrink the sample if K+W steps would exceed ~150 s
-    dt_probe, _, threads = cpu_port_run(min(n, 10_000_000), 2, 1)
+    nthr = host_threads(args)
+    dt_probe, _, threads = cpu_port_run(min(n, 10_000_000), 2, 1, threads=nthr)
     est = dt_probe * (n / min(n, 10_000_000)) * (args.steps + args.warmup)
     n_s = n if est <= 150 else max(1_000_000, int(n * 150 / est))
-    dt, steps, threads = cpu_port_run(n_s, args.steps, args.warmup)
+    dt, steps, threads = cpu_port_run(n_s, args.steps, args.warmup, threads=nthr)
     dt_full = dt * (n / n_s)
     val = 1.0 / dt_full
     sample = f"{steps} unfused FISTA iterations (14 vector passes each) on n={n_s} fp32" + ("" if n_s == n else f", time scaled by {n / n_s:.3g} to n={n}")
@@ -214,10 +232,11 @@ def run_b200(args):
         comm = LocalComm()
     lo, hi = shard_bounds(args.n, world)[rank]
     n = hi - lo
-    gen = torch.Generator(device="cuda").manual_seed(3 + rank)
-    x = torch.randn(n, device="cuda", generator=gen)
-    grad = torch.randn(n, device="cuda", generator=gen)
-    z_prev = torch.randn(n, device="cuda", generator=gen)
+    # synthetic data as a pure function of the GLOBAL element index (counter-based: csrc/util_kernels.cu, the generator of the CPU
+    # port's fill): every N works on the same n-vector, so the per-iteration scalars can be compared bit for bit across N
+    x, grad, z_prev = (torch.empty(n, device="cuda", dtype=torch.float32) for _ in range(3))
+    for buf, seed in ((x, 3), (z_prev, 4), (grad, 5)):
+        L.check(ctx.lib.pb_fill_counter(ctx.h, L.PB_F32, n, lo, seed, 1.0, ptr(buf)))
     z = torch.empty_like(x)
     x_next = torch.empty_like(x)
     desc = L.pb_prox(L.PB_PROX_L1, 0, LAMBDA, 0.0, None, None)
@@ -268,6 +287,8 @@ def run_b200(args):
         tm = solver.last_timing
         ms_total, kern_ms = tm["loop_ms"], tm["step_kernel_ms"] / max(1, tm["step_kernel_launches"])
         last_res_inf = float(solver.last_state.res_norm_inf)
+        parity = dict(solver.last_parity)
+        parity["g_z"] = float(solver.last_state.g_z)
         del zsol
     else:
         for _ in range(max(3, args.warmup)):
@@ -286,6 +307,7 @@ def run_b200(args):
         launches = ctx.launches() - launches0
         kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
         last_res_inf = sc.res_inf
+        parity = {"res_inf": sc.res_inf, "res_sq": sc.res_sq, "gdr": sc.gdr, "gsum": sc.gsum, "g_z": float(np.float32(LAMBDA) * np.float32(sc.gsum))}
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total, kern_ms], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -375,7 +397,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_s = args.n      # full size: a smaller sample would sit in the host's last-level cache and flatter the CPU
-        dt_s, steps_s, threads = cpu_port_run(n_s, 1000, 2, seconds_budget=args.cpu_seconds)
+        dt_s, steps_s, threads = cpu_port_run(n_s, 1000, 2, seconds_budget=args.cpu_seconds, threads=host_threads(args))
         cpu = {"value": 1.0 / (dt_s * args.n / n_s), "unit": "iterations/s", "cores": threads, "kind": "port",
                "sample": f"{steps_s} unfused iterations (14 vector passes) of the C port on n={n_s} fp32, time scaled x{args.n / n_s:.3g} to n={args.n}"}
 
@@ -392,7 +414,7 @@ def run_b200(args):
                        "loop": args.loop,
                        "n": args.n, "n_per_gpu": n, "parallelism": f"row-shard x{world}", "exchange": args.exchange, "l2": "inputs exceed L2 (5 x %.0f MB streams per GPU)" % (4 * n / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "kernel": "k_step<float, L1, EXTRAP> (pb_ffb_step)", "kernel_ms": kern_ms_max,
+                         "traffic": ncu_traffic(n), "kernel": "k_step<float, L1, EXTRAP> (pb_ffb_step)", "kernel_ms": kern_ms_max,
                          "algorithmic_bytes_per_launch": BYTES_PER_ELT * n, "peak_source": peak_src,
                          "note": ("kernel_ms = CUDA-event duration of the K2 launches inside the timed region. --loop native with the device exchange "
                                   "runs the pipelined driver (pb_solve look-ahead): K2 writes per-CTA partials and a 1-CTA kernel on a side stream "
@@ -406,6 +428,9 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "last_residual_inf": last_res_inf,
+            # rank-combined reductions of the LAST iteration (norm(res, Inf), norm(res)^2, dot(grad, res), sum|z|, g(z)): the data
+            # is a function of the global index and the sums are double-double, so these are bit-identical for N = 1, 2, 4, 8
+            "parity": parity,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -97,6 +97,10 @@ int pb_device_count(int* count);
  * and the context creates and owns a non-blocking stream. */
 int pb_ctx_create(int device, void* stream, int borrow_stream, pb_ctx** out);
 int pb_ctx_destroy(pb_ctx* ctx);
+/* Make the context's device the calling thread's current CUDA device.  Kernels are launched on the context's stream, which belongs
+ * to that device: a host thread that drives several contexts on different GPUs (or a fresh thread, which starts on device 0) calls
+ * this before using a context.  pb_solve / pb_panoc_solve do it themselves (and restore the previous device). */
+int pb_ctx_make_current(pb_ctx* ctx);
 void* pb_ctx_stream(pb_ctx* ctx);
 int pb_ctx_sync(pb_ctx* ctx);
 /* Device address of the PB_NSCALARS-double scalar block (so a host framework can all-gather it in place). */
@@ -111,8 +115,11 @@ enum {
   PB_OPT_UNROLL = 2,        /* 16-byte packs in flight per thread and input stream: 0 = default, or 1, 2, 4, 8       */
   PB_OPT_STEP_IMPL = 3,     /* fused step implementation: 0 = default, 1 = register (LDG) pipeline, 2 = TMA bulk-copy
                                shared-memory ring                                                                 */
-  PB_OPT_FUSED_EXCHANGE = 4 /* 1: pb_fb_step / pb_ffb_step also perform the per-iteration exchange (pb_xchg_*) in their
+  PB_OPT_FUSED_EXCHANGE = 4,/* 1: pb_fb_step / pb_ffb_step also perform the per-iteration exchange (pb_xchg_*) in their
                                last CTA, so the iteration needs no collective launch, memcpy or stream sync       */
+  PB_OPT_PERSISTENT = 5     /* pb_solve on cache-resident dense least squares (m*n*sizeof <= 8 MB): 0 = auto (whole solve
+                               in one persistent cooperative kernel, csrc/persist.cu), -1 = never (one kernel per
+                               operation), 1..32 = persistent on at most that many CTAs.  Results do not depend on it */
 };
 int pb_ctx_set_option(pb_ctx* ctx, int option, int value);
 /* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
@@ -128,6 +135,9 @@ int64_t pb_ctx_launch_count(pb_ctx* ctx);
 #define PB_MAX_WORLD 8
 int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out);
 int pb_xchg_connect(pb_ctx* ctx, const void* all_handles /* world x PB_IPC_HANDLE_BYTES, rank order */);
+/* Single-process form (one host process drives all GPUs, one host thread per context): the n contexts
+ * belong to this process, ctxs[r] initialised with pb_xchg_init(ctxs[r], r, n, NULL); peers are reached by peer access. */
+int pb_xchg_connect_local(pb_ctx** ctxs, int n);
 int pb_xchg_shutdown(pb_ctx* ctx);
 /* Enqueue a stand-alone exchange of the current scalar block (for reads that do not follow a fused step). */
 int pb_exchange(pb_ctx* ctx);
@@ -144,6 +154,10 @@ int pb_upload(pb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);  
 int pb_download(pb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* synchronises */
 int pb_copy(pb_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);       /* `copy`, FFB:74, FB:66 */
 int pb_memset_zero(pb_ctx* ctx, void* dst_dev, size_t bytes);                     /* `zero(x)` */
+/* out[i] = scale * u(offset + i), u in [-1, 1) a counter-based (splitmix64) function of the GLOBAL index: a row shard holds
+ * exactly the values of the unsharded vector (bench.py: identical synthetic data for every number of GPUs and for the CPU
+ * port, oracle/c/fb_port.c: port_fill). */
+int pb_fill_counter(pb_ctx* ctx, int dtype, int64_t n, int64_t offset, uint64_t seed, double scale, void* out);
 /* Copy the device scalar block to `out` (PB_NSCALARS doubles) and synchronise the stream. */
 int pb_read_scalars(pb_ctx* ctx, double* out);
 
@@ -306,11 +320,15 @@ typedef struct pb_solve_result {
   int64_t backtracks;
   double gamma, f_x, g_z, res_inf;
   int32_t warned_small_gamma;   /* fb_tools.jl:59-61 would have warned                                         */
-  int32_t pad;
+  int32_t persistent_ctas;      /* > 0: the solve ran as ONE persistent kernel on that many CTAs (csrc/persist.cu)    */
   void *x, *grad, *z, *z_prev;  /* which of the caller's buffers hold the final state fields (buffers are swapped) */
   double loop_ms;               /* opts->profile: CUDA-event time from the first kernel of init to the last kernel  */
   double step_kernel_ms;        /* opts->profile: summed CUDA-event time of the timed fused-step launches            */
   int64_t step_kernel_launches; /* opts->profile: how many launches that sum covers (at most 4096)                   */
+  /* rank-combined reductions of the final state's fused step, rounded once from their double-double sums: norm(res)^2,
+   * dot(grad_f_x, res) (the f_model terms, fb_tools.jl:3-5) and sum|z| (L1) / sum_g scal_g*||y_g|| (L21).  Identical
+   * for every sharding of the iterate -- bench.py prints them as its cross-N parity fingerprint. */
+  double res_sq, gdr, gsum;
 } pb_solve_result;
 
 /* x holds copy(x0) on entry.  grad, z, scratch: n-vectors.  z_prev, x_next: FFB only.  grad_z: adaptive FB only. */

@@ -34,6 +34,16 @@ int port_num_threads(void) {
 #endif
 }
 
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the baseline sets its thread count explicitly so that it uses
+ * the same host cores whether bench.py is started directly or under torchrun. */
+void port_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 enum { PORT_PROX_L1 = 1, PORT_PROX_BOX = 2 };
 
 #define DEFINE_PORT(T, SUF, FABS)                                                                                    \

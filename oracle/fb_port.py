@@ -28,11 +28,18 @@ def lib():
             f.restype = None
             f.argtypes = [C.c_int64, C.c_void_p, C.c_uint64, ct]
         _lib.port_num_threads.restype = C.c_int
+        _lib.port_set_threads.restype = None
+        _lib.port_set_threads.argtypes = [C.c_int]
     return _lib
 
 
 def num_threads():
     return int(lib().port_num_threads())
+
+
+def set_threads(n):
+    """Explicit OpenMP thread count (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().port_set_threads(int(n))
 
 
 def _p(a):

@@ -544,6 +544,8 @@ def _native_solve(alg, it):
 
     st._sc = _Sc
     it.backtracks = int(res.backtracks)
+    alg.last_persistent_ctas = int(res.persistent_ctas)     # > 0: the whole solve was ONE persistent kernel (csrc/persist.cu)
+    alg.last_parity = {"res_inf": float(res.res_inf), "res_sq": float(res.res_sq), "gdr": float(res.gdr), "gsum": float(res.gsum)}
     alg.last_iteration, alg.last_state = it, st
     sol = _like_input(it.x0, st.z)
     # host-side wall clock of the phases (pb_solve returns after its last scalar read, i.e. with the stream drained)

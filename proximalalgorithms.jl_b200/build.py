@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 INCLUDE = os.path.join(ROOT, "include")
 LIBNAME = "libproxb200.so"
-SOURCES = ["ctx.cu", "step_kernels.cu", "step_tma.cu", "lsq_kernels.cu", "xchg.cu", "solve.cu", "qn_kernels.cu", "dr_kernels.cu", "lsq_prox.cu", "tv_kernels.cu", "stencil_kernels.cu", "panoc_solve.cu"]
+SOURCES = ["ctx.cu", "step_kernels.cu", "step_tma.cu", "lsq_kernels.cu", "xchg.cu", "solve.cu", "qn_kernels.cu", "dr_kernels.cu", "lsq_prox.cu", "tv_kernels.cu", "stencil_kernels.cu", "panoc_solve.cu", "util_kernels.cu", "persist.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -44,11 +44,29 @@ def _stamp():
             h.update(name.encode())
             h.update(open(path, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(sorted(EXTRA_FLAGS.items())).encode())
     return h.hexdigest()
 
 
 def lib_path():
     return os.path.join(LIBDIR, LIBNAME)
+
+
+# extra nvcc flags per source.  persist.cu runs the driver loop's scalar arithmetic (solve_scalar.h) ON the device: like the
+# host build (-ffp-contract=off) it must round every product and sum separately; explicit fma() calls are unaffected.
+EXTRA_FLAGS = {"persist.cu": ["-fmad=false"]}
+
+
+def _obj_stamp(src):
+    """Hash of one source, every header it may include and its flags: only stale objects are recompiled."""
+    h = hashlib.sha256()
+    names = [src] + sorted(n for n in os.listdir(CSRC) if n.endswith((".cuh", ".h")))
+    for name in names:
+        h.update(name.encode())
+        h.update(open(os.path.join(CSRC, name), "rb").read())
+    h.update(open(os.path.join(INCLUDE, "proxb200.h"), "rb").read())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_FLAGS.get(src, [])).encode())
+    return h.hexdigest()
 
 
 def build(force=False, verbose=False):
@@ -62,7 +80,11 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        ostamp_file = obj + ".stamp"
+        ostamp = _obj_stamp(src)
+        if not force and os.path.exists(obj) and os.path.exists(ostamp_file) and open(ostamp_file).read() == ostamp:
+            return obj
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(os.path.join(LIBDIR, src.replace(".cu", ".ptxas.log")), "w") as fh:
@@ -71,6 +93,8 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}:\n{log}")
         if verbose:
             print(log)
+        with open(ostamp_file, "w") as fh:
+            fh.write(ostamp)
         return obj
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:

@@ -14,6 +14,7 @@
 #define PB_MAX_CTAS 4096        // upper bound on grid size of reducing kernels (workspace rows)
 #define PB_MAX_SUMS 4           // double-double sums a kernel may reduce
 #define PB_MAX_MAXS 2           // max-reductions a kernel may reduce
+#define PB_MAX_DEVICES 64       // device ordinals with their own per-device caches (function attributes, occupancy)
 
 // Reduction workspace in device memory: a ticket counter and per-CTA partials laid out [quantity][cta].
 struct PbWorkspace {
@@ -38,6 +39,7 @@ struct pb_ctx {
   int stream_hints;    // -1 auto, 0 off, 1 on
   int unroll;          // 0 = default
   int step_impl;       // 0 = default, 1 = register pipeline, 2 = TMA bulk ring
+  int persist_mode;    // PB_OPT_PERSISTENT: 0 auto, -1 never, k > 0 at most k CTAs
   double* scalars_dev;   // active scalar block (own or caller supplied)
   double* scalars_own;
   double* scalars_host;  // pinned mirror
@@ -57,6 +59,7 @@ struct pb_ctx {
   unsigned int xchg_seq;                    // last sequence number issued
   int xchg_rank, xchg_world;                // world == 0: not initialised
   int xchg_connected;
+  int xchg_local;                           // peers are contexts of this process (pb_xchg_connect_local): nothing to cudaIpcClose
   int xchg_fused;                           // K1/K2 push in-kernel
   int xchg_pending;                         // a launched kernel will publish xchg_seq
   int64_t xchg_pending_launch;              // value of `launches` right after that kernel's launch
@@ -75,6 +78,19 @@ void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want);
 // Wait for one specific exchange (by sequence number) in the pinned landing zone; rows_out: world x PB_NSCALARS doubles.
 int pb_xchg_wait_seq(pb_ctx* ctx, unsigned int seq, double* rows_out, double timeout_s);
 int pb_step_defer(pb_ctx* ctx, int on);
+
+// Make the context's device current for the calling thread for the lifetime of the guard (a process that drives several GPUs has
+// one host thread per context; a fresh thread starts on device 0).  Restores the previous device on exit.
+struct PbDeviceGuard {
+  int prev;
+  bool switched;
+  explicit PbDeviceGuard(const pb_ctx* ctx) : prev(-1), switched(false) {
+    if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~PbDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
 
 void pb_set_error(const char* fmt, ...);
 int pb_ensure_scratch(pb_ctx* ctx, size_t bytes);

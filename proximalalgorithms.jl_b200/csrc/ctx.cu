@@ -110,6 +110,12 @@ extern "C" int pb_ctx_destroy(pb_ctx* c) {
   return PB_OK;
 }
 
+extern "C" int pb_ctx_make_current(pb_ctx* c) {
+  PB_REQUIRE(c != nullptr, "null context");
+  PB_CHECK_CUDA(cudaSetDevice(c->device));
+  return PB_OK;
+}
+
 extern "C" void* pb_ctx_stream(pb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" double* pb_ctx_scalars_dev(pb_ctx* c) { return c ? c->scalars_dev : nullptr; }
 extern "C" int64_t pb_ctx_launch_count(pb_ctx* c) { return c ? c->launches : 0; }
@@ -138,6 +144,10 @@ extern "C" int pb_ctx_set_option(pb_ctx* c, int option, int value) {
     case PB_OPT_STEP_IMPL:
       PB_REQUIRE(value >= 0 && value <= 2, "step implementation must be 0, 1 or 2");
       c->step_impl = value;
+      return PB_OK;
+    case PB_OPT_PERSISTENT:
+      PB_REQUIRE(value >= -1 && value <= 32, "persistent mode must be -1, 0 or 1..32");
+      c->persist_mode = value;
       return PB_OK;
     case PB_OPT_FUSED_EXCHANGE:
       PB_REQUIRE(value == 0 || value == 1, "fused exchange must be 0 or 1");

@@ -8,10 +8,11 @@
 //              folded in index order by a second kernel that also subtracts b and reduces ||r||^2 (double-double).
 //   gradient : warp per column (columns are contiguous), lanes stride over rows, shuffle tree.
 #include "common.cuh"
+#include "lsq_order.h"
 
 #define GEMV_ROWS 128  // rows per CTA of the residual kernel
-#define GEMV_CL 4      // column lanes per CTA
-#define GEMV_UNROLL 8
+#define GEMV_CL PB_GEMV_CL          // column lanes per CTA
+#define GEMV_UNROLL PB_GEMV_UNROLL
 
 // partial[(chunk*nblk + k)*mb + i] = sum_{j in chunk} A_k[i, j] * x_k[j]
 template <typename T>
@@ -265,24 +266,17 @@ static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
   // Column chunking is a function of the BLOCK SHAPE ONLY (never of nblk or the SM count): the summation order of every
   // r_i is then the same on any GPU and for any sharding of the blocks over ranks, so a block-sharded run reproduces the
   // single-GPU bits.  ceil(nb/64) columns per chunk, clamped to [32, 4096]  ->  <= 64 chunks (more only for nb > 262144).
-  int64_t chunk_cols = (nb + 63) / 64;
-  if (chunk_cols < GEMV_CL * GEMV_UNROLL) chunk_cols = GEMV_CL * GEMV_UNROLL;
-  if (chunk_cols > 4096) chunk_cols = 4096;
-  int64_t nchunk = nb > 0 ? (nb + chunk_cols - 1) / chunk_cols : 1;
+  // (the rule itself lives in lsq_order.h, shared with the persistent driver kernel)
+  const PbLsqOrder ord = pb_lsq_order(sizeof(T), nblk, mb, nb, lda, blk_stride, A, nullptr);
+  const int64_t chunk_cols = ord.chunk_cols, nchunk = ord.nchunk;
   PB_REQUIRE(nchunk <= 65535, "too many column chunks for one launch");
   (void)row_tiles;
   PB_REQUIRE(nblk <= 65535, "too many blocks for one launch (nblk <= 65535)");
   int rc = pb_ensure_scratch(ctx, (size_t)nchunk * M * sizeof(T));
   if (rc != PB_OK) return rc;
   T* partial = static_cast<T*>(ctx->scratch);
-  constexpr int VEC = 16 / sizeof(T);
-  const int64_t npk = mb / VEC;
-  const bool sub_ok = mb < 64 && mb % VEC == 0 && lda % VEC == 0 && blk_stride % VEC == 0 && pb_aligned16(A) &&
-                      nblk * nchunk <= 0x7fffffffLL;
-  if (sub_ok) {
-    const int kp = npk <= 1 ? 1 : (npk <= 2 ? 2 : 4);
-    int lpc = 1;
-    while ((int64_t)lpc * kp < npk) lpc <<= 1;
+  if (ord.n_sub) {
+    const int kp = ord.n_kp, lpc = ord.n_lpc;
 #define PB_LAUNCH_NSUB(L, KP_)                                                                                              \
   k_gemv_n_sub<T, L, KP_><<<(unsigned)(nblk * nchunk), PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk, \
                                                                                   chunk_cols, nchunk)
@@ -316,15 +310,10 @@ static int gradient_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
                       const T* r, T* grad) {
   const int64_t ncols = nblk * nb;
   if (ncols == 0) return PB_OK;
-  constexpr int VEC = 16 / sizeof(T);
-  const int64_t npk = mb / VEC;
-  const bool sub_ok = mb > 0 && mb % VEC == 0 && lda % VEC == 0 && blk_stride % VEC == 0 && npk <= 32 * 4 &&
-                      pb_aligned16(A) && pb_aligned16(r);
-  if (sub_ok) {
+  const PbLsqOrder ord = pb_lsq_order(sizeof(T), nblk, mb, nb, lda, blk_stride, A, r);
+  if (ord.t_sub) {
     // packs per lane: 1 or 2 for very short columns (whole column in one lane, 4 columns in flight), else 4 with LPC lanes
-    const int kp = npk <= 1 ? 1 : (npk <= 2 ? 2 : 4);
-    int lpc = 1;
-    while ((int64_t)lpc * kp < npk) lpc <<= 1;
+    const int kp = ord.t_kp, lpc = ord.t_lpc;
     // chunk the columns of a block so that the grid covers the machine ~8x (~32x for the very short columns, whose CTAs
     // are cheap: a finer partition shortens the partial last wave)
     int64_t chunks = ((int64_t)ctx->sm_count * (kp <= 2 ? 32 : 8) + nblk - 1) / nblk;

@@ -486,6 +486,7 @@ extern "C" int pb_panoc_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth
   PB_REQUIRE(ctx->xchg_world <= 1, "pb_panoc_solve is single-GPU (the L-BFGS recursion needs un-sharded dot products)");
   PB_REQUIRE(o->A == nullptr || (o->Am > 0 && o->An == n), "A must be Am x n");
   memset(out, 0, sizeof(*out));
+  PbDeviceGuard dev_guard(ctx);
   const int64_t m = o->A ? o->Am : n;
   if (dtype == PB_F32) {
     Panoc<float> s;

@@ -15,6 +15,11 @@
 #include <limits>
 
 #include "common.cuh"
+#include "solve_scalar.h"
+
+bool pb_persist_eligible(const pb_ctx* ctx, int dtype, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o);   // persist.cu
+int pb_persist_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o, void* x,
+                     void* grad, void* z, void* z_prev, pb_solve_result* out);
 
 namespace {
 
@@ -88,59 +93,6 @@ int read_comb_seq(pb_ctx* ctx, unsigned int seq, Comb* c) {
   return PB_OK;
 }
 
-// square root IN R (numpy's sqrt of an R scalar): sqrtf for float, sqrt for double
-inline float rs(float v) { return sqrtf(v); }
-inline double rs(double v) { return sqrt(v); }
-
-template <typename R>
-struct Nesterov {       // src/accel/nesterov.jl; same roundings as nesterov.py
-  int kind;
-  R m, stepsize, theta;   // adaptive
-  R t;                    // fixed
-  long k;                 // simple
-  R constant;
-  void init(int kind_, R mf, R constant_beta) {
-    kind = kind_;
-    m = mf;
-    stepsize = R(-1);
-    theta = R(-1);
-    t = R(1);
-    k = 1;
-    constant = constant_beta;
-  }
-  R next(R gamma) {
-    switch (kind) {
-      case PB_SEQ_FIXED: {             // nesterov.jl:14-17
-        const R t_next = (R(1) + rs(R(1) + R(4) * (t * t))) / R(2);
-        const R beta = (t - R(1)) / t_next;
-        t = t_next;
-        return beta;
-      }
-      case PB_SEQ_SIMPLE: {            // nesterov.jl:36
-        const R beta = R(k - 1) / R(k + 2);
-        ++k;
-        return beta;
-      }
-      case PB_SEQ_CONSTANT:            // nesterov.jl:51-54
-        return constant;
-      default: {                       // AdaptiveNesterovSequence, nesterov.jl:89-103
-        if (stepsize < 0) {
-          stepsize = gamma;
-          theta = m > 0 ? rs(m * gamma) : R(1);
-        }
-        const R th2 = theta * theta;
-        const R b = th2 / stepsize - m;
-        const R delta = b * b + (R(4) * th2) / (stepsize * gamma);
-        const R theta_n = (gamma * (rs(delta) - b)) / R(2);
-        const R beta = ((gamma * theta) * (R(1) - theta)) / (stepsize * theta_n + gamma * th2);
-        stepsize = gamma;
-        theta = theta_n;
-        return beta;
-      }
-    }
-  }
-};
-
 template <typename R>
 struct Solver {
   pb_ctx* ctx;
@@ -160,13 +112,10 @@ struct Solver {
   static const int kMaxStepEvents = 4096;
   cudaEvent_t ev_loop[2];
   cudaEvent_t* ev_step;
-  int n_step_events;
+  int n_step_events, n_created;
   bool profile;
 
-  static R sq_half(double sum_sq) {        // norm(v)^2/2 with sqrt-then-square rounding (benchmark/benchmarks.jl:16)
-    const R nr = (R)sqrt(sum_sq);
-    return (nr * nr) / R(2);
-  }
+  static R sq_half(double sum_sq) { return pb_sq_half<R>(sum_sq); }   // norm(v)^2/2, sqrt-then-square (benchmark/benchmarks.jl:16)
   R f_value(const Comb& c) const {
     switch (f->kind) {
       case PB_F_LSQ_DENSE: return sq_half(c.local_aux);
@@ -178,10 +127,7 @@ struct Solver {
     if (g->kind == PB_PROX_L1 || g->kind == PB_PROX_L21) return (R)g->p0 * (R)c.gsum;
     return R(0);
   }
-  static R f_model(R fx, double gdr, double res_sq, R Lc) {     // fb_tools.jl:3-5
-    const R nr = (R)sqrt(res_sq);
-    return (fx - (R)gdr) + (Lc / R(2)) * (nr * nr);
-  }
+  static R f_model(R fx, double gdr, double res_sq, R Lc) { return pb_f_model<R>(fx, gdr, res_sq, Lc); }   // fb_tools.jl:3-5
 
   int residual(const void* v) {     // f's residual pass at v; the value is Deferred in the AUX slot
     switch (f->kind) {
@@ -216,7 +162,16 @@ struct Solver {
   }
   int step(const void* xin, const void* gr, void* zout, bool extrap, R beta) { return step_to(xin, gr, z_prev, zout, x_next, extrap, beta); }
   int step_to(const void* xin, const void* gr, const void* zp, void* zout, void* xnext_out, bool extrap, R beta) {
-    const bool timed = profile && n_step_events < kMaxStepEvents;
+    // events are created on first use (the adaptive paths launch more steps than maxit: one per backtrack)
+    bool timed = profile && n_step_events < kMaxStepEvents;
+    if (timed && n_step_events == n_created) {
+      if (cudaEventCreate(&ev_step[2 * n_created]) == cudaSuccess && cudaEventCreate(&ev_step[2 * n_created + 1]) == cudaSuccess) {
+        ++n_created;
+      } else {
+        cudaGetLastError();
+        timed = profile = false;          // stop timing rather than record on an invalid handle
+      }
+    }
     if (timed) cudaEventRecord(ev_step[2 * n_step_events], ctx->stream);
     const int rc = extrap ? pb_ffb_step(ctx, dtype, n, xin, gr, zp, (double)gamma, (double)beta, g, nullptr, zout, nullptr, xnext_out)
                           : pb_fb_step(ctx, dtype, n, xin, gr, (double)gamma, g, nullptr, zout, nullptr);
@@ -267,32 +222,29 @@ struct Solver {
     lazy_value = f->kind == PB_F_LINEAR && !adaptive && o->gamma > 0;
     profile = o->profile != 0;
     ev_step = nullptr;
-    n_step_events = 0;
+    n_step_events = n_created = 0;
+    const bool profile_req = profile;
     if (profile) {
       ev_step = new cudaEvent_t[2 * kMaxStepEvents];
-      const int64_t want = o->maxit < kMaxStepEvents ? o->maxit : kMaxStepEvents;
-      for (int64_t i = 0; i < 2 * want; ++i) cudaEventCreate(&ev_step[i]);
       cudaEventCreate(&ev_loop[0]);
       cudaEventCreate(&ev_loop[1]);
       cudaEventRecord(ev_loop[0], ctx->stream);
     }
     rc = run_loop(out);
-    if (profile) {
-      if (rc == PB_OK) {
+    if (profile_req) {
+      if (rc == PB_OK && profile) {
         cudaEventSynchronize(ev_loop[1]);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev_loop[0], ev_loop[1]);
         out->loop_ms = ms;
         double tot = 0.0;
         for (int i = 0; i < n_step_events; ++i) {
-          cudaEventElapsedTime(&ms, ev_step[2 * i], ev_step[2 * i + 1]);
-          tot += ms;
+          if (cudaEventElapsedTime(&ms, ev_step[2 * i], ev_step[2 * i + 1]) == cudaSuccess) tot += ms;
         }
         out->step_kernel_ms = tot;
         out->step_kernel_launches = n_step_events;
       }
-      const int64_t want = o->maxit < kMaxStepEvents ? o->maxit : kMaxStepEvents;
-      for (int64_t i = 0; i < 2 * want; ++i) cudaEventDestroy(ev_step[i]);
+      for (int i = 0; i < 2 * n_created; ++i) cudaEventDestroy(ev_step[i]);
       cudaEventDestroy(ev_loop[0]);
       cudaEventDestroy(ev_loop[1]);
       delete[] ev_step;
@@ -458,7 +410,7 @@ struct Solver {
 
   int finish(pb_solve_result* out, int64_t k) {
     int rc;
-    if (profile) cudaEventRecord(ev_loop[1], ctx->stream);     // the K iterations end here
+    if (ev_step) cudaEventRecord(ev_loop[1], ctx->stream);     // the K iterations end here
     if (lazy_value) {                    // f(x) of the final state (LinearFunction: <c, x>)
       if ((rc = pb_dot(ctx, dtype, n, f->b, x))) return rc;
       Comb c;
@@ -470,6 +422,9 @@ struct Solver {
     out->f_x = (double)f_x;
     out->g_z = (double)g_z;
     out->res_inf = sc.res_inf;
+    out->res_sq = sc.res_sq;
+    out->gdr = sc.gdr;
+    out->gsum = sc.gsum;
     out->backtracks = backtracks;
     out->warned_small_gamma = warned;
     out->x = x;
@@ -497,6 +452,9 @@ extern "C" int pb_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, c
              "pb_solve supports the single-pass prox kinds (Zero, NormL1, IndBox, NormL21)");
   PB_REQUIRE(f->kind != PB_F_LSQ_DENSE || ctx->xchg_world <= 1, "dense least squares is single-GPU in pb_solve (column shards need a vector all-gather)");
   memset(out, 0, sizeof(*out));
+  PbDeviceGuard dev_guard(ctx);
+  // cache-resident dense least squares: the whole loop runs on the device in one persistent kernel (persist.cu), same results
+  if (pb_persist_eligible(ctx, dtype, f, g, o) && n == f->n && n > 0) return pb_persist_solve(ctx, dtype, n, f, g, o, x, grad, z, z_prev, out);
   if (dtype == PB_F32) {
     Solver<float> s{ctx, dtype, n, f, g, o, x, grad, z, z_prev, x_next, grad_z, scratch};
     return s.run(out);

@@ -11,6 +11,7 @@
 template <typename T, int PROX, bool EXTRAP, int VEC, int UNROLL, bool HINT>
 __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
   constexpr bool COMP = sizeof(T) == 8;
+  constexpr bool VECP = PROX == PB_PROX_BOX || PROX == PB_PROX_SQRL2;   // prox kinds with an optional per-element vector in lo_v
   constexpr int64_t TILE = (int64_t)PB_BLOCK * VEC * UNROLL;
   const T* __restrict__ x = static_cast<const T*>(p.x);
   const T* __restrict__ g = static_cast<const T*>(p.grad);
@@ -26,21 +27,23 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
   const int64_t n = p.n;
   const int64_t ntiles = n / TILE;
 
-  Acc<3, 1> acc;
+  Acc<3, 1> acc, pk;
   acc.clear();
+  pk.clear();
 
   // one 16-byte pack: compute, store, accumulate
   auto do_pack = [&](int64_t i, const Pack<T, VEC>& xq, const Pack<T, VEC>& gq, const Pack<T, VEC>& zq) {
     Pack<T, VEC> lo, hi, yv, zn, rv, xn;
-    if (PROX == PB_PROX_BOX && lov) lo = ld_pack<T, VEC, false>(lov + i);
+    if (VECP && lov) lo = ld_pack<T, VEC, false>(lov + i);
     if (PROX == PB_PROX_BOX && hiv) hi = ld_pack<T, VEC, false>(hiv + i);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      const T l = (PROX == PB_PROX_BOX && lov) ? lo.v[e] : pa;
+      const T l = (VECP && lov) ? lo.v[e] : pa;
       const T h = (PROX == PB_PROX_BOX && hiv) ? hi.v[e] : pb;
       StepElem<T, PROX, EXTRAP>::template run<COMP>(xq.v[e], gq.v[e], EXTRAP ? zq.v[e] : T(0), l, h, gamma, beta, yv.v[e],
-                                                    zn.v[e], rv.v[e], xn.v[e], acc);
+                                                    zn.v[e], rv.v[e], xn.v[e], COMP ? acc : pk, lov != nullptr);
     }
+    if constexpr (!COMP) fold_pack<PROX>(acc, pk);
     st_pack<T, VEC, HINT>(zo + i, zn);
     if constexpr (EXTRAP) st_pack<T, VEC, HINT>(xo + i, xn);
     if (yo) st_pack<T, VEC, HINT>(yo + i, yv);
@@ -75,11 +78,12 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
   // ragged tail (< VEC elements), element-wise
   for (int64_t i = rem_start + rem_packs * VEC + (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * PB_BLOCK) {
-    const T l = (PROX == PB_PROX_BOX && lov) ? lov[i] : pa;
+    const T l = (VECP && lov) ? lov[i] : pa;
     const T h = (PROX == PB_PROX_BOX && hiv) ? hiv[i] : pb;
     T yv, zn, rv, xn;
     StepElem<T, PROX, EXTRAP>::template run<COMP>(x[i], g[i], EXTRAP ? zp[i] : T(0), l, h, gamma, beta, yv, zn, rv, xn,
-                                                  acc);
+                                                  COMP ? acc : pk, lov != nullptr);
+    if constexpr (!COMP) fold_pack<PROX>(acc, pk);
     zo[i] = zn;
     if constexpr (EXTRAP) xo[i] = xn;
     if (yo) yo[i] = yv;
@@ -545,7 +549,9 @@ static int resident_grid(pb_ctx* ctx, K kern, int* occ_cache, int64_t work_per_c
 template <typename T, int PROX, bool EXTRAP, int UNROLL>
 static int launch_step_u(pb_ctx* ctx, const StepParams& p, bool vec_ok, bool hint) {
   constexpr int VEC = 16 / sizeof(T);
-  static int occ[3] = {0, 0, 0};
+  // occupancy is queried on the context's device: one cache row per device ordinal
+  static int occ_dev[PB_MAX_DEVICES][3] = {};
+  int* occ = occ_dev[ctx->device < PB_MAX_DEVICES ? ctx->device : 0];
   if (vec_ok) {
     if (hint) {
       auto kern = k_step<T, PROX, EXTRAP, VEC, UNROLL, true>;
@@ -609,6 +615,7 @@ static int launch_step_deferred(pb_ctx* ctx, StepParams p, const pb_prox* g, boo
     case PB_PROX_ZERO: rc = launch_step_t<T, PB_PROX_ZERO, EXTRAP>(ctx, p, vec_ok); break;
     case PB_PROX_L1: rc = launch_step_t<T, PB_PROX_L1, EXTRAP>(ctx, p, vec_ok); break;
     case PB_PROX_BOX: rc = launch_step_t<T, PB_PROX_BOX, EXTRAP>(ctx, p, vec_ok); break;
+    case PB_PROX_SQRL2: rc = launch_step_t<T, PB_PROX_SQRL2, EXTRAP>(ctx, p, vec_ok); break;
     default: rc = launch_step_t<T, PB_PROX_SCALE, EXTRAP>(ctx, p, vec_ok); break;
   }
   if (rc != PB_OK) return rc;
@@ -644,6 +651,14 @@ static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool ve
     case PB_PROX_SCALE:
       p.a = g->p0;
       break;
+    case PB_PROX_SQRL2: {           // den = 1 + gamma*lambda in the element type (two roundings, as pb_dr_step / pb_prox_apply)
+      const T gl = mul_rn_host(gamma, (T)g->p0);
+      volatile T den = T(1) + gl;
+      p.b = (double)den;
+      p.lo_v = g->v0;
+      if (p.lo_v && !pb_aligned16(p.lo_v)) vec_ok = false;
+      break;
+    }
     default:
       pb_set_error("unknown prox kind %d", g->kind);
       return PB_EINVAL;
@@ -680,6 +695,8 @@ static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool ve
       return launch_step_t<T, PB_PROX_L1, EXTRAP>(ctx, p, vec_ok);
     case PB_PROX_BOX:
       return launch_step_t<T, PB_PROX_BOX, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_SQRL2:
+      return launch_step_t<T, PB_PROX_SQRL2, EXTRAP>(ctx, p, vec_ok);
     default:
       return launch_step_t<T, PB_PROX_SCALE, EXTRAP>(ctx, p, vec_ok);
   }

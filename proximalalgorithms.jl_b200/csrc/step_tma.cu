@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(TMA_BLOCK) k_step_tma(StepParams p) {
     for (int64_t it = 0; it < pre; ++it) issue_load(it);
   }
 
-  Acc<3, 1> acc;
+  Acc<3, 1> acc, pk;
   acc.clear();
+  pk.clear();
 
   for (int64_t it = 0; it < my_tiles; ++it) {
     const int s = (int)(it % STAGES);
@@ -123,8 +124,9 @@ __global__ void __launch_bounds__(TMA_BLOCK) k_step_tma(StepParams p) {
     for (int e = 0; e < VEC; ++e) {
       T yv, rv;
       StepElem<T, PROX, EXTRAP>::template run<COMP>(xv.v[e], gv.v[e], EXTRAP ? zv.v[e] : T(0), pa, pb, gamma, beta, yv,
-                                                    zn.v[e], rv, xn.v[e], acc);
+                                                    zn.v[e], rv, xn.v[e], COMP ? acc : pk);
     }
+    if constexpr (!COMP) fold_pack<PROX>(acc, pk);
     *reinterpret_cast<Pack<T, VEC>*>(sout + tid * VEC) = zn;
     if constexpr (EXTRAP) *reinterpret_cast<Pack<T, VEC>*>(sout + TILE + tid * VEC) = xn;
     fence_proxy_async();
@@ -139,13 +141,27 @@ __global__ void __launch_bounds__(TMA_BLOCK) k_step_tma(StepParams p) {
     }
   }
 
-  // ragged tail (< TILE elements): plain element-wise path, spread over the grid
-  for (int64_t i = ntiles * TILE + (int64_t)blockIdx.x * TMA_BLOCK + tid; i < n; i += (int64_t)gridDim.x * TMA_BLOCK) {
-    T yv, zn, rv, xn;
-    StepElem<T, PROX, EXTRAP>::template run<COMP>(gx[i], gg[i], EXTRAP ? gzp[i] : T(0), pa, pb, gamma, beta, yv, zn, rv,
-                                                  xn, acc);
-    gz[i] = zn;
-    if constexpr (EXTRAP) gxn[i] = xn;
+  // ragged tail (< TILE elements): plain path, spread over the grid, one 16-byte pack per thread and trip so that float sums are
+  // grouped exactly as everywhere else (fold_pack); the last < VEC elements are single-element groups like in k_step
+  for (int64_t q = ntiles * TMA_BLOCK + (int64_t)blockIdx.x * TMA_BLOCK + tid; q * VEC < n; q += (int64_t)gridDim.x * TMA_BLOCK) {
+    const bool whole = q * VEC + VEC <= n;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int64_t i = q * VEC + e;
+      if (i < n) {
+        T yv, zn, rv, xn;
+        StepElem<T, PROX, EXTRAP>::template run<COMP>(gx[i], gg[i], EXTRAP ? gzp[i] : T(0), pa, pb, gamma, beta, yv, zn, rv,
+                                                      xn, COMP ? acc : pk);
+        gz[i] = zn;
+        if constexpr (EXTRAP) gxn[i] = xn;
+        if constexpr (!COMP) {
+          if (!whole) fold_pack<PROX>(acc, pk);
+        }
+      }
+    }
+    if constexpr (!COMP) {
+      if (whole) fold_pack<PROX>(acc, pk);
+    }
   }
   if (tid == 0) bulk_wait_all();   // staging tiles must outlive the last bulk stores
 
@@ -166,11 +182,13 @@ static int launch_tma(pb_ctx* ctx, const StepParams& p) {
   constexpr int TILE = TMA_BLOCK * VEC;
   constexpr int NIN = EXTRAP ? 3 : 2, NOUT = EXTRAP ? 2 : 1;
   constexpr size_t smem = (size_t)(STAGES * NIN + 3 * NOUT) * TILE * sizeof(T) + STAGES * sizeof(uint64_t);
-  static bool attr_done = false;
+  // cudaFuncSetAttribute is per device: one flag per device ordinal (a single process may drive several GPUs)
+  static bool attr_done[PB_MAX_DEVICES] = {};
   auto kern = k_step_tma<T, PROX, EXTRAP, STAGES>;
-  if (!attr_done) {
+  const int dev = ctx->device < PB_MAX_DEVICES ? ctx->device : 0;
+  if (!attr_done[dev] || ctx->device >= PB_MAX_DEVICES) {
     PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   const int grid = pb_stream_grid(ctx, TILE, p.n, EXTRAP ? 3 : 2);   // co-resident by construction (<= 72 KB smem per CTA)
   kern<<<grid, TMA_BLOCK, smem, ctx->stream>>>(p);

@@ -80,18 +80,51 @@ extern "C" int pb_xchg_connect(pb_ctx* ctx, const void* all_handles) {
   return PB_OK;
 }
 
+// Single-process form of pb_xchg_connect (SURVEY.md section 8b "Threading": one host process drives all GPUs): the n contexts
+// live in THIS process (cudaIpc cannot open a handle in the exporting process), so the peers' exchange buffers are reached
+// through plain peer access.  ctxs[r] must have been initialised with pb_xchg_init(ctxs[r], r, n, NULL).  Contexts may share
+// a device (used by the single-GPU tests of the sharded path: their streams run concurrently).
+extern "C" int pb_xchg_connect_local(pb_ctx** ctxs, int n) {
+  PB_REQUIRE(ctxs != nullptr && n >= 1 && n <= PB_MAX_RANKS, "need 1 <= n <= 8 contexts");
+  for (int r = 0; r < n; ++r) {
+    PB_REQUIRE(ctxs[r] != nullptr && ctxs[r]->xchg_world == n && ctxs[r]->xchg_rank == r && ctxs[r]->xchg_own != nullptr,
+               "ctxs[r] must be initialised with pb_xchg_init(ctxs[r], r, n, ...)");
+  }
+  for (int r = 0; r < n; ++r) {
+    PB_CHECK_CUDA(cudaSetDevice(ctxs[r]->device));
+    for (int q = 0; q < n; ++q) {
+      if (ctxs[q]->device != ctxs[r]->device) {
+        int can = 0;
+        PB_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device));
+        if (!can) {
+          pb_set_error("pb_xchg_connect_local: device %d cannot access device %d", ctxs[r]->device, ctxs[q]->device);
+          return PB_EUNSUPPORTED;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PB_CHECK_CUDA(e);
+        cudaGetLastError();
+      }
+      ctxs[r]->xchg_peer[q] = ctxs[q]->xchg_own;
+    }
+    ctxs[r]->xchg_connected = 1;
+    ctxs[r]->xchg_local = 1;
+  }
+  return PB_OK;
+}
+
 extern "C" int pb_xchg_shutdown(pb_ctx* ctx) {
   if (!ctx || ctx->xchg_world == 0) return PB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (int r = 0; r < ctx->xchg_world; ++r)
-    if (r != ctx->xchg_rank && ctx->xchg_peer[r]) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
+    if (r != ctx->xchg_rank && ctx->xchg_peer[r] && !ctx->xchg_local) cudaIpcCloseMemHandle(ctx->xchg_peer[r]);
   if (ctx->xchg_own) cudaFree(ctx->xchg_own);
   if (ctx->xchg_host_words) cudaFreeHost(ctx->xchg_host_words);
   ctx->xchg_own = nullptr;
   ctx->xchg_host_words = nullptr;
   ctx->xchg_world = 0;
   ctx->xchg_connected = 0;
+  ctx->xchg_local = 0;
   ctx->xchg_fused = 0;
   ctx->xchg_pending = 0;
   return PB_OK;
