@@ -359,6 +359,11 @@ typedef struct pb_panoc_result {
 int pb_panoc_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_panoc_opts* opts,
                    const void* x0, void* z_out, pb_panoc_result* result);
 
+/* Diagnostic of the persistent solver (csrc/persist.cu): clock64() cycles CTA 0 spent per phase in the last pb_solve that ran
+ * persistently with opts->profile = 1.  out8: 0 A*v chunk partials, 1 grid barrier + scalar fold, 2 r = sum of partials - b and
+ * ||r||^2, 3 A'r, 4 fused step, 5 everything else, 6-7 unused. */
+int pb_persist_phase_cycles(pb_ctx* ctx, int64_t* out8);
+
 /* ---- host-buffer convenience (the "plugin call with HOST buffers"): upload x, grad, z_prev, run K2, download z, x_next
  * and the scalar block.  All host pointers; temporary device buffers are cached in the context. */
 int pb_ffb_step_host(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev,

@@ -140,6 +140,7 @@ SIGNATURES = {
     "pb_solve": (_i, [_vp, _i, _i64, C.POINTER(pb_smooth), _pp, C.POINTER(pb_solve_opts), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                       C.POINTER(pb_solve_result)]),
     "pb_panoc_solve": (_i, [_vp, _i, _i64, C.POINTER(pb_smooth), _pp, C.POINTER(pb_panoc_opts), _vp, _vp, C.POINTER(pb_panoc_result)]),
+    "pb_persist_phase_cycles": (_i, [_vp, C.POINTER(C.c_int64)]),
     "pb_ffb_step_host": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _d, _d, _pp, _vp, _vp, C.POINTER(C.c_double)]),
 }
 

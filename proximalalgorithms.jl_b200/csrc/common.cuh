@@ -40,6 +40,7 @@ struct pb_ctx {
   int unroll;          // 0 = default
   int step_impl;       // 0 = default, 1 = register pipeline, 2 = TMA bulk ring
   int persist_mode;    // PB_OPT_PERSISTENT: 0 auto, -1 never, k > 0 at most k CTAs
+  long long persist_cycles[8];   // per-phase clock64() totals of the last profiled persistent solve
   double* scalars_dev;   // active scalar block (own or caller supplied)
   double* scalars_own;
   double* scalars_host;  // pinned mirror

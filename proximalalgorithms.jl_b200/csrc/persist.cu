@@ -51,33 +51,84 @@ struct PersistParams {
   // cross-CTA workspace (global): chunk partials [2][nchunk][m], reduction partials [2][G][PS_SCAL], barrier counter
   void* partial;
   double* scal;
-  unsigned int* bar;
+  unsigned int* bar;                     // one arrival flag per CTA (epoch number), 32 bytes apart
   int ns_max;                            // slice capacity (elements) of one shared-memory slot
+  int timing;                            // 1: CTA 0 accumulates clock64() per phase into `cycles`
+  long long* cycles;                     // [PS_NPHASE]
   pb_solve_result* result;               // device copy, written by CTA 0
 };
+
+enum { PS_PH_GEMV_N = 0, PS_PH_BARRIER, PS_PH_COMBINE, PS_PH_GEMV_T, PS_PH_STEP, PS_PH_OTHER, PS_NPHASE = 8 };
+#define PS_FLAG_STRIDE 8                 // unsigned ints between two CTAs' arrival flags
 
 // ---------------------------------------------------------------------------------------------------------------------
 // grid barrier: monotone counter, release/acquire at gpu scope.  All CTAs are co-resident (cooperative launch).
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ps_grid_barrier(unsigned int* bar, unsigned int& epoch) {
-  __syncthreads();
-  epoch += 1;
+// Arrival: every CTA owns one flag; it stores the epoch number there (release) once its data for this epoch is written.  Waiting:
+// lane c of warp 0 polls CTA c's flag (acquire), so the G flags are watched in parallel and nothing serialises on one address.
+__device__ __forceinline__ void ps_arrive(unsigned int* bar, unsigned int epoch) {
+  __syncthreads();                       // this CTA's partials are written
   if (gridDim.x > 1 && threadIdx.x == 0) {
-    const unsigned int target = epoch * gridDim.x;
     __threadfence();
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + (size_t)blockIdx.x * PS_FLAG_STRIDE), "r"(epoch) : "memory");
+  }
+}
+__device__ __forceinline__ void ps_wait_warp0(const unsigned int* bar, unsigned int epoch) {   // called by warp 0 only
+  if (gridDim.x > 1 && threadIdx.x < gridDim.x) {
+    const unsigned int* f = bar + (size_t)threadIdx.x * PS_FLAG_STRIDE;
     unsigned int v;
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-    } while ((int)(v - target) < 0);
-    __threadfence();
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    } while ((int)(v - epoch) < 0);
   }
-  __syncthreads();
+  __syncwarp();
 }
 
+// cross-CTA data goes through L2 (L1 is not coherent); with ONE CTA the same buffers live in shared memory
 template <typename T>
-__device__ __forceinline__ void st_cg(T* p, T v) {
-  __stcg(p, v);
+__device__ __forceinline__ void ps_st(T* p, T v, bool one) {
+  if (one)
+    *p = v;
+  else
+    __stcg(p, v);
+}
+template <typename T>
+__device__ __forceinline__ T ps_ld(const T* p, bool one) {
+  return one ? *p : __ldcg(p);
+}
+
+// Block reduction restricted to the warps that hold data (`active` threads, tid < active): the double-double shuffle trees are
+// FP64-pipe bound, and a slice of 32 columns keeps 8 of the 512 threads busy.  Result valid in thread 0; `red`: 16 x 8 doubles.
+template <int NSUM, int NMAX>
+__device__ __forceinline__ void ps_block_reduce(Acc<NSUM, NMAX>& a, int active, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int naw = (active + 31) >> 5;
+  if (naw < 1) naw = 1;
+  if (warp < naw) {
+    warp_reduce<NSUM, NMAX>(a);
+    if (lane == 0 && naw > 1) {
+#pragma unroll
+      for (int k = 0; k < NSUM; ++k) {
+        red[warp * 8 + 2 * k] = a.s[k].hi;
+        red[warp * 8 + 2 * k + 1] = a.s[k].lo;
+      }
+#pragma unroll
+      for (int k = 0; k < NMAX; ++k) red[warp * 8 + 6 + k] = a.m[k];
+    }
+  }
+  if (naw > 1) {
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NSUM; ++k) {
+        a.s[k].hi = lane < naw ? red[lane * 8 + 2 * k] : 0.0;
+        a.s[k].lo = lane < naw ? red[lane * 8 + 2 * k + 1] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < NMAX; ++k) a.m[k] = lane < naw ? red[lane * 8 + 6 + k] : 0.0;
+      warp_reduce<NSUM, NMAX>(a);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -130,7 +181,7 @@ __device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ v, 
         s += shp[512 + tid];
         s += shp[1024 + tid];
         s += shp[1536 + tid];
-        st_cg(partial + (int64_t)ch * m + row, s);
+        ps_st(partial + (int64_t)ch * m + row, s, gridDim.x == 1);
       }
       __syncthreads();
     }
@@ -197,7 +248,7 @@ __device__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ v, i
         T s = sh[i];
 #pragma unroll
         for (int w = 1; w < 8; ++w) s += sh[w * W + i];
-        st_cg(partial + (int64_t)ch * m + i, s);
+        ps_st(partial + (int64_t)ch * m + i, s, gridDim.x == 1);
       }
     }
     __syncthreads();
@@ -207,25 +258,32 @@ __device__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ v, i
 // phase 2 (every CTA, after the barrier): r_i = (sum over chunks, in chunk order) - b_i into shared memory; returns
 // ||r||^2 rounded once from its double-double sum (what the host reads as AUX hi + lo), in every thread.
 template <typename T>
-__device__ double ps_combine_r(const PersistParams& p, const T* partial, T* r_sh, double* bc) {
+__device__ double ps_combine_r(const PersistParams& p, const T* partial, T* r_sh, double* bc, double* red) {
   constexpr bool COMP = sizeof(T) == 8;
   const T* __restrict__ b = static_cast<const T*>(p.b);
   const int64_t m = p.m;
   const int nchunk = (int)p.ord.nchunk;
+  const bool one = gridDim.x == 1;
   Acc<1, 1> acc;
   acc.clear();
   for (int64_t i = threadIdx.x; i < m; i += PS_THREADS) {
-    T s = __ldcg(partial + i);
+    T s = ps_ld(partial + i, one);
     int c = 1;
-    for (; c + 3 < nchunk; c += 4) {
-      const T t0 = __ldcg(partial + (int64_t)c * m + i), t1 = __ldcg(partial + (int64_t)(c + 1) * m + i);
-      const T t2 = __ldcg(partial + (int64_t)(c + 2) * m + i), t3 = __ldcg(partial + (int64_t)(c + 3) * m + i);
-      s += t0;
-      s += t1;
-      s += t2;
-      s += t3;
+    for (; c + 15 < nchunk; c += 16) {          // 16 independent L2 loads in flight, added in chunk order
+      T t[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) t[u] = ps_ld(partial + (int64_t)(c + u) * m + i, one);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += t[u];
     }
-    for (; c < nchunk; ++c) s += __ldcg(partial + (int64_t)c * m + i);
+    for (; c + 3 < nchunk; c += 4) {
+      T t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = ps_ld(partial + (int64_t)(c + u) * m + i, one);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s += t[u];
+    }
+    for (; c < nchunk; ++c) s += ps_ld(partial + (int64_t)c * m + i, one);
     const T rv = b ? sub_rn(s, __ldg(b + i)) : s;
     r_sh[i] = rv;
     if (COMP)
@@ -233,7 +291,7 @@ __device__ double ps_combine_r(const PersistParams& p, const T* partial, T* r_sh
     else
       acc.s[0].hi = __fma_rn((double)rv, (double)rv, acc.s[0].hi);
   }
-  block_reduce<1, 1, PS_THREADS>(acc);
+  ps_block_reduce<1, 1>(acc, (int)(m < PS_THREADS ? m : PS_THREADS), red);
   if (threadIdx.x == 0) bc[0] = acc.s[0].hi + acc.s[0].lo;
   __syncthreads();
   const double aux = bc[0];
@@ -293,7 +351,7 @@ __device__ void ps_gemv_t(const PersistParams& p, const T* __restrict__ r_sh, T*
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T, int PROX, bool EXTRAP>
 __device__ void ps_step_t(const PersistParams& p, const T* x, const T* g, const T* zp, T gamma, T beta, T* z, T* xn, int64_t j0,
-                          int ns, double* scal_out) {
+                          int ns, double* scal_out, double* red) {
   constexpr bool COMP = sizeof(T) == 8;
   const T* __restrict__ lov = static_cast<const T*>(p.lo_v);
   const T* __restrict__ hiv = static_cast<const T*>(p.hi_v);
@@ -331,32 +389,34 @@ __device__ void ps_step_t(const PersistParams& p, const T* x, const T* g, const 
       if (whole) fold_pack<PROX>(acc, pk);
     }
   }
-  block_reduce<3, 1, PS_THREADS>(acc);
+  const int packs = (ns + VEC - 1) / VEC;
+  ps_block_reduce<3, 1>(acc, packs < PS_THREADS ? packs : PS_THREADS, red);
   if (threadIdx.x == 0) {
+    const bool one = gridDim.x == 1;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      __stcg(scal_out + 2 * k, acc.s[k].hi);
-      __stcg(scal_out + 2 * k + 1, acc.s[k].lo);
+      ps_st(scal_out + 2 * k, acc.s[k].hi, one);
+      ps_st(scal_out + 2 * k + 1, acc.s[k].lo, one);
     }
-    __stcg(scal_out + 6, acc.m[0]);
+    ps_st(scal_out + 6, acc.m[0], one);
   }
 }
 
 template <typename T>
 __device__ void ps_step(const PersistParams& p, const T* x, const T* g, const T* zp, T gamma, T beta, bool extrap, T* z, T* xn,
-                        int64_t j0, int ns, double* scal_out) {
+                        int64_t j0, int ns, double* scal_out, double* red) {
   switch (p.prox_kind) {
     case PB_PROX_L1:
-      if (extrap) ps_step_t<T, PB_PROX_L1, true>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out);
-      else ps_step_t<T, PB_PROX_L1, false>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out);
+      if (extrap) ps_step_t<T, PB_PROX_L1, true>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out, red);
+      else ps_step_t<T, PB_PROX_L1, false>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out, red);
       break;
     case PB_PROX_BOX:
-      if (extrap) ps_step_t<T, PB_PROX_BOX, true>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out);
-      else ps_step_t<T, PB_PROX_BOX, false>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out);
+      if (extrap) ps_step_t<T, PB_PROX_BOX, true>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out, red);
+      else ps_step_t<T, PB_PROX_BOX, false>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out, red);
       break;
     default:
-      if (extrap) ps_step_t<T, PB_PROX_ZERO, true>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out);
-      else ps_step_t<T, PB_PROX_ZERO, false>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out);
+      if (extrap) ps_step_t<T, PB_PROX_ZERO, true>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out, red);
+      else ps_step_t<T, PB_PROX_ZERO, false>(p, x, g, zp, gamma, beta, z, xn, j0, ns, scal_out, red);
       break;
   }
 }
@@ -365,26 +425,32 @@ struct PsComb {
   double gsum, res_sq, gdr, res_inf;
 };
 
-// after the barrier: fold the G CTAs' reduction partials (warp 0, fixed shuffle tree), broadcast to every thread
-__device__ PsComb ps_fold(const double* scal, double* bc) {
+// The grid barrier and the fold of the G CTAs' reduction partials in one: warp 0 waits for the G arrival flags (lane c watches CTA c),
+// lane c then loads CTA c's partials, a fixed shuffle tree folds them, and the rounded scalars are broadcast through shared memory.
+// want_scal = false: barrier only (phases that publish just a partial product).
+__device__ PsComb ps_wait_fold(const PersistParams& p, unsigned int epoch, const double* scal, bool want_scal, double* bc) {
+  const bool one = gridDim.x == 1;
   if (threadIdx.x < 32) {
-    Acc<3, 1> a;
-    a.clear();
-    if (threadIdx.x < gridDim.x) {
-      const double* s = scal + (size_t)threadIdx.x * PS_SCAL;
+    ps_wait_warp0(p.bar, epoch);
+    if (want_scal) {
+      Acc<3, 1> a;
+      a.clear();
+      if (threadIdx.x < gridDim.x) {
+        const double* s = scal + (size_t)threadIdx.x * PS_SCAL;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        a.s[k].hi = __ldcg(s + 2 * k);
-        a.s[k].lo = __ldcg(s + 2 * k + 1);
+        for (int k = 0; k < 3; ++k) {
+          a.s[k].hi = ps_ld(s + 2 * k, one);
+          a.s[k].lo = ps_ld(s + 2 * k + 1, one);
+        }
+        a.m[0] = ps_ld(s + 6, one);
       }
-      a.m[0] = __ldcg(s + 6);
-    }
-    warp_reduce<3, 1>(a);
-    if (threadIdx.x == 0) {
-      bc[0] = a.s[0].hi + a.s[0].lo;
-      bc[1] = a.s[1].hi + a.s[1].lo;
-      bc[2] = a.s[2].hi + a.s[2].lo;
-      bc[3] = a.m[0];
+      if (!one) warp_reduce<3, 1>(a);
+      if (threadIdx.x == 0) {
+        bc[0] = a.s[0].hi + a.s[0].lo;
+        bc[1] = a.s[1].hi + a.s[1].lo;
+        bc[2] = a.s[2].hi + a.s[2].lo;
+        bc[3] = a.m[0];
+      }
     }
   }
   __syncthreads();
@@ -393,7 +459,7 @@ __device__ PsComb ps_fold(const double* scal, double* bc) {
   c.res_sq = bc[1];
   c.gdr = bc[2];
   c.res_inf = bc[3];
-  __syncthreads();
+  __syncthreads();                       // everyone has read the broadcast before its next writer runs
   return c;
 }
 
@@ -406,6 +472,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   constexpr bool COMP = sizeof(T) == 8;
   extern __shared__ __align__(16) unsigned char ps_smem[];
   __shared__ double bc[8];
+  __shared__ double red[16 * 8];
+  __shared__ double scal_sh[2 * PS_SCAL];
+  __shared__ long long cyc[PS_NPHASE];
   T* slot[PS_NSLOT];
   for (int k = 0; k < PS_NSLOT; ++k) slot[k] = reinterpret_cast<T*>(ps_smem) + (size_t)k * p.ns_max;
   T* r_sh = reinterpret_cast<T*>(ps_smem) + (size_t)PS_NSLOT * p.ns_max;
@@ -423,9 +492,28 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   if (j1 < j0) j1 = j0;
   const int ns = (int)(j1 - j0);
   const int64_t m = p.m;
+  // cross-CTA buffers, double buffered by epoch parity: L2 (global) when several CTAs cooperate, shared memory when one does
   T* partial_buf[2] = {static_cast<T*>(p.partial), static_cast<T*>(p.partial) + (size_t)nchunk * m};
   double* scal_buf[2] = {p.scal, p.scal + (size_t)PS_MAX_CTAS * PS_SCAL};
+  if (G == 1) {
+    partial_buf[0] = shp + 2048;
+    partial_buf[1] = partial_buf[0] + (size_t)nchunk * m;
+    scal_buf[0] = scal_sh;
+    scal_buf[1] = scal_sh + PS_SCAL;
+  }
   unsigned int epoch = 0;
+  long long t_last = 0;
+  if (p.timing && cta == 0 && tid == 0) {
+    for (int k = 0; k < PS_NPHASE; ++k) cyc[k] = 0;
+    t_last = clock64();
+  }
+  auto lap = [&](int phase) {                 // CTA 0, thread 0: cycles since the previous lap go to `phase`
+    if (p.timing && cta == 0 && tid == 0) {
+      const long long t = clock64();
+      cyc[phase] += t - t_last;
+      t_last = t;
+    }
+  };
 
   // slots (pointers are swapped exactly where the reference swaps its vectors)
   T *X = slot[0], *GR = slot[1], *Z = slot[2], *ZP = slot[3], *W1 = slot[4], *W2 = slot[5];
@@ -438,16 +526,41 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   __syncthreads();
 
   auto publish_Av = [&](const T* v) {          // chunk partials of A v into the buffer of the NEXT barrier
+    lap(PS_PH_OTHER);
     T* part = partial_buf[(epoch + 1) & 1];
     if (p.ord.n_sub)
       ps_gemv_n_sub<T>(p, v, j0, ch0, ch1, part, shp);
     else
       ps_gemv_n_rows<T>(p, v, j0, ch0, ch1, part, shp);
+    lap(PS_PH_GEMV_N);
   };
   auto scal_slot = [&]() { return scal_buf[(epoch + 1) & 1] + (size_t)cta * PS_SCAL; };
-  auto barrier = [&]() { ps_grid_barrier(p.bar, epoch); };
-  auto combine = [&]() { return ps_combine_r<T>(p, partial_buf[epoch & 1], r_sh, bc); };
-  auto fold = [&]() { return ps_fold(scal_buf[epoch & 1], bc); };
+  // grid barrier (+ fold of the reduction partials published for it)
+  auto sync_fold = [&](bool want_scal) {
+    lap(PS_PH_OTHER);
+    epoch += 1;
+    ps_arrive(p.bar, epoch);
+    const PsComb c = ps_wait_fold(p, epoch, scal_buf[epoch & 1], want_scal, bc);
+    lap(PS_PH_BARRIER);
+    return c;
+  };
+  auto combine = [&]() {
+    const double a = ps_combine_r<T>(p, partial_buf[epoch & 1], r_sh, bc, red);
+    lap(PS_PH_COMBINE);
+    return a;
+  };
+  auto gemv_t = [&](T* gout) {
+    lap(PS_PH_OTHER);
+    ps_gemv_t<T>(p, r_sh, gout, j0, j1);
+    __syncthreads();
+    lap(PS_PH_GEMV_T);
+  };
+  auto step = [&](const T* xs, const T* gs, const T* zps, R gam, R bet, bool extrap, T* zs, T* xns) {
+    lap(PS_PH_OTHER);
+    ps_step<T>(p, xs, gs, zps, gam, bet, extrap, zs, xns, j0, ns, scal_slot(), red);
+    __syncthreads();
+    lap(PS_PH_STEP);
+  };
   auto f_value = [&](double aux) { return pb_sq_half<R>(aux); };
   auto g_value = [&](const PsComb& c) { return p.prox_kind == PB_PROX_L1 ? (R)p.p0 * (R)c.gsum : R(0); };
 
@@ -462,9 +575,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
 
   // ---- init: forward_backward.jl:65-84 / fast_forward_backward.jl:73-97 ----
   publish_Av(X);
-  barrier();
+  (void)sync_fold(false);
   aux = combine();                              // r = A x - b
-  ps_gemv_t<T>(p, r_sh, GR, j0, j1);            // grad f(x)
+  gemv_t(GR);                                   // grad f(x)
   bool fx_pending = true;
   if (p.gamma <= 0) {                           // fb_tools.jl:7-12 with A = I
     f_x = f_value(aux);
@@ -472,10 +585,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
     for (int e = tid; e < ns; e += PS_THREADS) W2[e] = add_rn(X[e], T(1));
     __syncthreads();
     publish_Av(W2);
-    barrier();
+    (void)sync_fold(false);
     (void)combine();
-    ps_gemv_t<T>(p, r_sh, Z, j0, j1);           // z is free at this point: holds grad f(x + 1)
-    __syncthreads();
+    gemv_t(Z);                                  // z is free at this point: holds grad f(x + 1)
     Acc<1, 1> a;
     a.clear();
     for (int e = tid; e < ns; e += PS_THREADS) {
@@ -486,15 +598,14 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
       else
         a.s[0].hi = __fma_rn((double)d, (double)d, a.s[0].hi);
     }
-    block_reduce<1, 1, PS_THREADS>(a);
+    ps_block_reduce<1, 1>(a, ns < PS_THREADS ? ns : PS_THREADS, red);
     if (tid == 0) {
       double* so = scal_slot();
-      __stcg(so + 0, a.s[0].hi);
-      __stcg(so + 1, a.s[0].lo);
-      for (int k = 2; k < 7; ++k) __stcg(so + k, 0.0);
+      ps_st(so + 0, a.s[0].hi, G == 1);
+      ps_st(so + 1, a.s[0].lo, G == 1);
+      for (int k = 2; k < 7; ++k) ps_st(so + k, 0.0, G == 1);
     }
-    barrier();
-    const PsComb c2 = fold();
+    const PsComb c2 = sync_fold(true);
     const int64_t n_glob = p.n_global > 0 ? p.n_global : p.n;
     const R lower = (R)sqrt(c2.gsum) / (R)sqrt((double)n_glob);
     gamma = R(1) / lower;
@@ -511,11 +622,9 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   }
   const bool fused_extrap = fast && !adaptive;
   if (fused_extrap) beta_next = seq.next(gamma);
-  ps_step<T>(p, X, GR, ZP, gamma, beta_next, fused_extrap, Z, W1, j0, ns, scal_slot());
-  __syncthreads();
+  step(X, GR, ZP, gamma, beta_next, fused_extrap, Z, W1);
   publish_Av(fused_extrap ? W1 : Z);            // the product the next operation needs rides on the same barrier
-  barrier();
-  sc = fold();
+  sc = sync_fold(true);
   aux_n = combine();
   if (fx_pending) f_x = f_value(aux);
   g_z = g_value(sc);
@@ -524,26 +633,18 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   auto backtrack = [&](bool want_grad, R& f_z_out) {
     const R eps = sizeof(T) == 4 ? (R)1.1920928955078125e-07 : (R)2.220446049250313e-16;
     R f_upp = pb_f_model<R>(f_x, sc.gdr, sc.res_sq, R(1) / gamma);
-    if (want_grad) {
-      ps_gemv_t<T>(p, r_sh, W1, j0, j1);        // grad f(z)
-      __syncthreads();
-    }
+    if (want_grad) gemv_t(W1);                  // grad f(z)
     R f_z = f_value(aux_n);
     R tol = R(10) * eps * (R(1) + (R)fabs((double)f_z));
     while (f_z > f_upp + tol && gamma >= min_gamma) {
       gamma = gamma * red_gamma;
-      ps_step<T>(p, X, GR, ZP, gamma, R(0), false, Z, W1, j0, ns, scal_slot());
-      __syncthreads();
+      step(X, GR, ZP, gamma, R(0), false, Z, W1);
       publish_Av(Z);
-      barrier();
-      sc = fold();
+      sc = sync_fold(true);
       aux_n = combine();
       g_z = g_value(sc);
       f_upp = pb_f_model<R>(f_x, sc.gdr, sc.res_sq, R(1) / gamma);
-      if (want_grad) {
-        ps_gemv_t<T>(p, r_sh, W1, j0, j1);
-        __syncthreads();
-      }
+      if (want_grad) gemv_t(W1);
       f_z = f_value(aux_n);
       tol = R(10) * eps * (R(1) + (R)fabs((double)f_z));
       ++backtracks;
@@ -568,14 +669,11 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
       } else {
         T* t = X; X = Z; Z = t;
         aux = aux_n;                              // r = A x - b was published with the previous step
-        ps_gemv_t<T>(p, r_sh, GR, j0, j1);
-        __syncthreads();
+        gemv_t(GR);
       }
-      ps_step<T>(p, X, GR, ZP, gamma, R(0), false, Z, W1, j0, ns, scal_slot());
-      __syncthreads();
+      step(X, GR, ZP, gamma, R(0), false, Z, W1);
       publish_Av(Z);
-      barrier();
-      sc = fold();
+      sc = sync_fold(true);
       aux_n = combine();
       if (!adaptive) f_x = f_value(aux);
       g_z = g_value(sc);
@@ -589,27 +687,22 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
         T* t = ZP; ZP = Z; Z = t;                 // :136
         __syncthreads();
         publish_Av(X);
-        barrier();
+        (void)sync_fold(false);
         aux = combine();
-        ps_gemv_t<T>(p, r_sh, GR, j0, j1);
-        __syncthreads();
-        ps_step<T>(p, X, GR, ZP, gamma, R(0), false, Z, W1, j0, ns, scal_slot());
-        __syncthreads();
+        gemv_t(GR);
+        step(X, GR, ZP, gamma, R(0), false, Z, W1);
         publish_Av(Z);
       } else {
         gamma = (R)p.gamma > 0 ? (R)p.gamma : gamma;
         T* t = X; X = W1; W1 = t;                 // :135, computed by the previous fused pass
         t = ZP; ZP = Z; Z = t;                    // :136
         aux = aux_n;
-        ps_gemv_t<T>(p, r_sh, GR, j0, j1);
-        __syncthreads();
+        gemv_t(GR);
         beta_next = seq.next(gamma);
-        ps_step<T>(p, X, GR, ZP, gamma, beta_next, true, Z, W1, j0, ns, scal_slot());
-        __syncthreads();
+        step(X, GR, ZP, gamma, beta_next, true, Z, W1);
         publish_Av(W1);
       }
-      barrier();
-      sc = fold();
+      sc = sync_fold(true);
       aux_n = combine();
       f_x = f_value(aux);
       g_z = g_value(sc);
@@ -641,6 +734,10 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
     out->gdr = sc.gdr;
     out->gsum = sc.gsum;
     out->warned_small_gamma = warned;
+    if (p.timing) {
+      lap(PS_PH_OTHER);
+      for (int q = 0; q < PS_NPHASE; ++q) p.cycles[q] = cyc[q];
+    }
   }
 }
 
@@ -669,7 +766,8 @@ static bool persist_plan(const pb_ctx* ctx, const pb_smooth* f, int want_ctas, P
   if (G < 1) G = 1;
   const int64_t ns_max = ((int64_t)(nchunk + G - 1) / G) * plan->ord.chunk_cols;
   const int64_t m_pad = (m + 3) & ~(int64_t)3;
-  const size_t smem = ((size_t)PS_NSLOT * ns_max + m_pad + 2048) * sizeof(T);
+  // one CTA: the chunk partials [2][nchunk][m] live in shared memory too (no trip through L2)
+  const size_t smem = ((size_t)PS_NSLOT * ns_max + m_pad + 2048 + (G == 1 ? (size_t)2 * nchunk * m : 0)) * sizeof(T);
   if (smem > 200 * 1024) return false;
   plan->ctas = G;
   plan->ns_max = (int)ns_max;
@@ -700,8 +798,9 @@ static int persist_run(pb_ctx* ctx, int64_t n, const pb_smooth* f, const pb_prox
   const size_t scal_off = (part_bytes + 255) & ~(size_t)255;
   const size_t scal_bytes = (size_t)2 * PS_MAX_CTAS * PS_SCAL * sizeof(double);
   const size_t bar_off = scal_off + scal_bytes;
-  const size_t res_off = bar_off + 256;
-  const size_t total = res_off + sizeof(pb_solve_result);
+  const size_t res_off = bar_off + (size_t)PS_MAX_CTAS * PS_FLAG_STRIDE * sizeof(unsigned int);
+  const size_t cyc_off = (res_off + sizeof(pb_solve_result) + 15) & ~(size_t)15;
+  const size_t total = cyc_off + PS_NPHASE * sizeof(long long);
   int rc = pb_ensure_scratch(ctx, total);
   if (rc != PB_OK) return rc;
   unsigned char* ws = static_cast<unsigned char*>(ctx->scratch);
@@ -739,6 +838,8 @@ static int persist_run(pb_ctx* ctx, int64_t n, const pb_smooth* f, const pb_prox
   p.scal = reinterpret_cast<double*>(ws + scal_off);
   p.bar = reinterpret_cast<unsigned int*>(ws + bar_off);
   p.ns_max = plan.ns_max;
+  p.timing = o->profile ? 1 : 0;
+  p.cycles = reinterpret_cast<long long*>(ws + cyc_off);
   p.result = reinterpret_cast<pb_solve_result*>(ws + res_off);
   auto kern = k_persist_solve<T>;
   static bool attr_done[PB_MAX_DEVICES][2] = {};
@@ -759,6 +860,7 @@ static int persist_run(pb_ctx* ctx, int64_t n, const pb_smooth* f, const pb_prox
   if (o->profile) PB_CHECK_CUDA(cudaEventRecord(ev[1], ctx->stream));
   pb_solve_result host;
   PB_CHECK_CUDA(cudaMemcpyAsync(&host, p.result, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream));
+  if (o->profile) PB_CHECK_CUDA(cudaMemcpyAsync(ctx->persist_cycles, p.cycles, PS_NPHASE * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   PB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = host;
   out->x = x;
@@ -780,4 +882,12 @@ int pb_persist_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, cons
                      void* grad, void* z, void* z_prev, pb_solve_result* out) {
   if (dtype == PB_F32) return persist_run<float>(ctx, n, f, g, o, x, grad, z, z_prev, out);
   return persist_run<double>(ctx, n, f, g, o, x, grad, z, z_prev, out);
+}
+
+// Diagnostic: clock64() cycles CTA 0 spent per phase in the last persistent solve run with opts->profile = 1
+// (0 A*v partials, 1 grid barrier + scalar fold, 2 r = sum of partials - b and ||r||^2, 3 A'r, 4 fused step, 5 everything else).
+extern "C" int pb_persist_phase_cycles(pb_ctx* ctx, int64_t* out8) {
+  PB_REQUIRE(ctx != nullptr && out8 != nullptr, "null argument");
+  for (int k = 0; k < PS_NPHASE; ++k) out8[k] = (int64_t)ctx->persist_cycles[k];
+  return PB_OK;
 }

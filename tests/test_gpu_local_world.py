@@ -112,7 +112,7 @@ def test_sharded_native_solve_in_one_process_equals_unsharded(P, alg, adaptive):
     b = rng.standard_normal(n).astype(T)
     x0 = rng.standard_normal(n).astype(T)
 
-    def run(world, r, lo, hi, out):
+    def run(world, r, lo, hi, out, ready):
         dev = torch.device("cuda", world.devs[r])
         m = hi - lo
         bd = torch.as_tensor(b[lo:hi]).to(dev)
@@ -120,6 +120,9 @@ def test_sharded_native_solve_in_one_process_equals_unsharded(P, alg, adaptive):
         bufs = [torch.empty(m, dtype=torch.float64, device=dev) for _ in range(8)]
         grad, z, zprev, xnext, gradz, scratch, sx, sz = bufs
         torch.cuda.synchronize(dev)
+        # every rank finishes its set-up (allocations, copies, device-wide synchronisation) BEFORE any rank enters the solve: a peer
+        # spinning inside an exchange must never be waited for by a device-wide operation of another rank (same rule as for NCCL)
+        ready.wait()
         f = L.pb_smooth(L.PB_F_SQDIST, 0, 0, m, 0, 0, 0, 0, None, bd.data_ptr(), None)
         g = L.pb_prox(L.PB_PROX_BOX, 0, -0.5, 0.5, None, None)
         pipelined = alg == L.PB_ALG_FFB and not adaptive
@@ -130,15 +133,18 @@ def test_sharded_native_solve_in_one_process_equals_unsharded(P, alg, adaptive):
                                 _p(gradz), _p(scratch), C.byref(res))
         if rc != 0:
             out[r] = RuntimeError(world.lib.pb_last_error().decode())
+            ready.abort()
             return
         keep = {t.data_ptr(): t for t in [x] + bufs}
+        ready.wait()
         out[r] = (int(res.iterations), int(res.backtracks), res.gamma, res.f_x, res.res_inf, keep[res.z].cpu().numpy().copy())
 
     def solve(P_):
         w = World(P_)
         try:
             out = [None] * P_
-            ths = [threading.Thread(target=run, args=(w, r, lo, hi, out)) for r, (lo, hi) in enumerate(shard_bounds(n, P_))]
+            ready = threading.Barrier(P_)
+            ths = [threading.Thread(target=run, args=(w, r, lo, hi, out, ready)) for r, (lo, hi) in enumerate(shard_bounds(n, P_))]
             for t in ths:
                 t.start()
             for t in ths:

@@ -47,9 +47,9 @@ def _same(a, b):
     (za, ia, _, sa, va, _), (zb, ib, _, sb, vb, _) = a, b
     assert ia == ib, (ia, ib)
     assert np.array_equal(za, zb, equal_nan=True)
-    assert sa == sb, (sa, sb)
+    assert np.array_equal(np.array(sa, dtype=np.float64), np.array(sb, dtype=np.float64), equal_nan=True), (sa, sb)
     for u, v in zip(va, vb):
-        assert torch.equal(u, v)
+        assert torch.equal(torch.nan_to_num(u, nan=1e300 if u.dtype == torch.float64 else 1e30), torch.nan_to_num(v, nan=1e300 if v.dtype == torch.float64 else 1e30))
 
 
 @pytest.mark.parametrize("name", ["tiny", "small", "medium"])
