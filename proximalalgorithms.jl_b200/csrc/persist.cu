@@ -30,7 +30,7 @@
 #define PS_THREADS 512
 #define PS_MAX_CTAS 32
 #define PS_NSLOT 6
-#define PS_SCAL 8            // doubles per CTA in the reduction exchange: 3 (hi, lo) pairs + 1 max + pad
+#define PS_SCAL 12           // doubles per CTA in the reduction exchange: 3 (hi, lo) pairs, 1 max, pad, (hi, lo) of this CTA's share of ||r||^2
 
 struct PersistParams {
   const void* A;
@@ -50,9 +50,12 @@ struct PersistParams {
   PbLsqOrder ord;
   // cross-CTA workspace (global): chunk partials [2][nchunk][m], reduction partials [2][G][PS_SCAL], barrier counter
   void* partial;
+  void* r_glob;                          // [m]: r = A v - b assembled from the CTAs' row shares (G > 1)
   double* scal;
   unsigned int* bar;                     // one arrival flag per CTA (epoch number), 32 bytes apart
   int ns_max;                            // slice capacity (elements) of one shared-memory slot
+  int shared_xchg;                       // 1: one CTA, the cross-CTA buffers live in shared memory
+  int a_in_smem;                         // 1: every CTA copies its column slice of A into shared memory at start
   int timing;                            // 1: CTA 0 accumulates clock64() per phase into `cycles`
   long long* cycles;                     // [PS_NPHASE]
   pb_solve_result* result;               // device copy, written by CTA 0
@@ -136,12 +139,12 @@ __device__ __forceinline__ void ps_block_reduce(Acc<NSUM, NMAX>& a, int active, 
 // element j lives at v[j - j0].  Two summation orders, exactly those of k_gemv_n_partial / k_gemv_n_sub (lsq_kernels.cu).
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ v, int64_t j0, int ch0, int ch1, T* partial, T* shp) {
+__device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ v, int64_t j0, int ch0,
+                               int ch1, T* partial, T* shp, bool one) {
   // row-per-thread order: 4 column lanes, each a sequential FMA chain over its columns j = c0 + cl, c0 + cl + 4, ...; the
   // lanes are then added ((l0 + l1) + l2) + l3.  512 threads = 128 rows x 4 lanes, four row tiles in flight per thread.
-  const T* __restrict__ A = static_cast<const T*>(p.A);
   const int tid = threadIdx.x, rl = tid & 127, cl = tid >> 7;
-  const int64_t m = p.m, lda = p.lda;
+  const int64_t m = p.m;
   for (int ch = ch0; ch < ch1; ++ch) {
     const int64_t c0 = (int64_t)ch * p.ord.chunk_cols;
     int64_t c1 = c0 + p.ord.chunk_cols;
@@ -155,8 +158,8 @@ __device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ v, 
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int64_t row = row0 + t * 128 + rl;
-          a0[t] = row < m ? __ldg(A + row + j * lda) : T(0);
-          a1[t] = row < m ? __ldg(A + row + (j + 4) * lda) : T(0);
+          a0[t] = row < m ? A[row + j * lda] : T(0);
+          a1[t] = row < m ? A[row + (j + 4) * lda] : T(0);
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -169,7 +172,7 @@ __device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ v, 
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int64_t row = row0 + t * 128 + rl;
-          if (row < m) acc[t] = fma(__ldg(A + row + j * lda), x0, acc[t]);
+          if (row < m) acc[t] = fma(A[row + j * lda], x0, acc[t]);
         }
       }
 #pragma unroll
@@ -181,7 +184,7 @@ __device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ v, 
         s += shp[512 + tid];
         s += shp[1024 + tid];
         s += shp[1536 + tid];
-        ps_st(partial + (int64_t)ch * m + row, s, gridDim.x == 1);
+        ps_st(partial + (int64_t)ch * m + row, s, one);
       }
       __syncthreads();
     }
@@ -189,17 +192,17 @@ __device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ v, 
 }
 
 template <typename T>
-__device__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ v, int64_t j0, int ch0, int ch1, T* partial, T* shp) {
+__device__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ v, int64_t j0, int ch0,
+                              int ch1, T* partial, T* shp, bool one) {
   // short-column order (m < 64): LPC lanes share a column, each owning up to KP 16-byte packs of it; a "virtual CTA" of 256
   // threads (8 warps) works one chunk exactly like k_gemv_n_sub does, two virtual CTAs side by side.
   constexpr int VEC = 16 / sizeof(T);
-  const T* __restrict__ A = static_cast<const T*>(p.A);
   const int lpc = p.ord.n_lpc, kp = p.ord.n_kp;
   const int vt = threadIdx.x & 255, vc = threadIdx.x >> 8;
   const int lane = vt & 31, warp = vt >> 5;
   const int cpw = 32 / lpc, sub = lane % lpc, colw = lane / lpc;
   const int64_t stride = (int64_t)8 * cpw;
-  const int64_t m = p.m, lda = p.lda, npk = m / VEC;
+  const int64_t m = p.m, npk = m / VEC;
   const int W = lpc * kp * VEC;                      // <= 64
   T* sh = shp + vc * (8 * 64);
   for (int chb = ch0; chb < ch1; chb += 2) {
@@ -226,7 +229,7 @@ __device__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ v, i
             const int64_t pk = sub + (int64_t)q * lpc;
             if (q < kp && pk < npk) {
 #pragma unroll
-              for (int e = 0; e < VEC; ++e) acc[q][e] = fma(__ldg(a + pk * VEC + e), xv, acc[q][e]);
+              for (int e = 0; e < VEC; ++e) acc[q][e] = fma(a[pk * VEC + e], xv, acc[q][e]);
             }
           }
         }
@@ -248,77 +251,65 @@ __device__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ v, i
         T s = sh[i];
 #pragma unroll
         for (int w = 1; w < 8; ++w) s += sh[w * W + i];
-        ps_st(partial + (int64_t)ch * m + i, s, gridDim.x == 1);
+        ps_st(partial + (int64_t)ch * m + i, s, one);
       }
     }
     __syncthreads();
   }
 }
 
-// phase 2 (every CTA, after the barrier): r_i = (sum over chunks, in chunk order) - b_i into shared memory; returns
-// ||r||^2 rounded once from its double-double sum (what the host reads as AUX hi + lo), in every thread.
+// phase 2: r_i = (sum over chunks, in chunk order) - b_i for rows [i0, i1); the dd sum of r_i^2 over those rows ends up in thread 0's
+// `acc`.  One CTA: all rows, r into shared memory.  Several CTAs: each assembles ITS share of the rows (the partials of all chunks
+// of a row are 8-byte loads from L2) and publishes it; after a second barrier everyone copies the m values of r.
 template <typename T>
-__device__ double ps_combine_r(const PersistParams& p, const T* partial, T* r_sh, double* bc, double* red) {
+__device__ void ps_combine_rows(const PersistParams& p, const T* partial, T* r_out, bool r_shared, int64_t i0, int64_t i1, bool one,
+                                Acc<1, 1>& acc, double* red) {
   constexpr bool COMP = sizeof(T) == 8;
   const T* __restrict__ b = static_cast<const T*>(p.b);
   const int64_t m = p.m;
   const int nchunk = (int)p.ord.nchunk;
-  const bool one = gridDim.x == 1;
-  Acc<1, 1> acc;
   acc.clear();
-  for (int64_t i = threadIdx.x; i < m; i += PS_THREADS) {
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += PS_THREADS) {
     T s = ps_ld(partial + i, one);
     int c = 1;
-    for (; c + 15 < nchunk; c += 16) {          // 16 independent L2 loads in flight, added in chunk order
-      T t[16];
+    for (; c + 7 < nchunk; c += 8) {            // 8 independent loads in flight, added in chunk order
+      T t[8];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) t[u] = ps_ld(partial + (int64_t)(c + u) * m + i, one);
+      for (int u = 0; u < 8; ++u) t[u] = ps_ld(partial + (int64_t)(c + u) * m + i, one);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) s += t[u];
-    }
-    for (; c + 3 < nchunk; c += 4) {
-      T t[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) t[u] = ps_ld(partial + (int64_t)(c + u) * m + i, one);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) s += t[u];
+      for (int u = 0; u < 8; ++u) s += t[u];
     }
     for (; c < nchunk; ++c) s += ps_ld(partial + (int64_t)c * m + i, one);
     const T rv = b ? sub_rn(s, __ldg(b + i)) : s;
-    r_sh[i] = rv;
+    ps_st(r_out + i, rv, r_shared);
     if (COMP)
       dd_add_prod(acc.s[0], (double)rv, (double)rv);
     else
       acc.s[0].hi = __fma_rn((double)rv, (double)rv, acc.s[0].hi);
   }
-  ps_block_reduce<1, 1>(acc, (int)(m < PS_THREADS ? m : PS_THREADS), red);
-  if (threadIdx.x == 0) bc[0] = acc.s[0].hi + acc.s[0].lo;
-  __syncthreads();
-  const double aux = bc[0];
-  __syncthreads();
-  return aux;
+  const int64_t rows = i1 - i0;
+  ps_block_reduce<1, 1>(acc, (int)(rows < PS_THREADS ? rows : PS_THREADS), red);
 }
 
 // grad_j = sum_i A[i, j] r_i for this CTA's columns, in the order of k_gemv_t (warp per column) or k_gemv_t_sub (LPC lanes per column)
 template <typename T>
-__device__ void ps_gemv_t(const PersistParams& p, const T* __restrict__ r_sh, T* g, int64_t j0, int64_t j1) {
+__device__ void ps_gemv_t(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ r_sh, T* g, int64_t j0, int64_t j1) {
   constexpr int VEC = 16 / sizeof(T);
-  const T* __restrict__ A = static_cast<const T*>(p.A);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t m = p.m, lda = p.lda;
+  const int64_t m = p.m;
   if (!p.ord.t_sub) {
     for (int64_t j = j0 + warp; j < j1; j += PS_THREADS / 32) {
       const T* __restrict__ a = A + j * lda;
       T acc = T(0);
       int64_t i = lane;
       for (; i + 96 < m; i += 128) {
-        const T a0 = __ldg(a + i), a1 = __ldg(a + i + 32), a2 = __ldg(a + i + 64), a3 = __ldg(a + i + 96);
+        const T a0 = a[i], a1 = a[i + 32], a2 = a[i + 64], a3 = a[i + 96];
         acc = fma(a0, r_sh[i], acc);
         acc = fma(a1, r_sh[i + 32], acc);
         acc = fma(a2, r_sh[i + 64], acc);
         acc = fma(a3, r_sh[i + 96], acc);
       }
-      for (; i < m; i += 32) acc = fma(__ldg(a + i), r_sh[i], acc);
+      for (; i < m; i += 32) acc = fma(a[i], r_sh[i], acc);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
       if (lane == 0) g[j - j0] = acc;
@@ -337,7 +328,7 @@ __device__ void ps_gemv_t(const PersistParams& p, const T* __restrict__ r_sh, T*
         const int64_t pk = sub + (int64_t)q * lpc;
         if (q < kp && pk < npk) {
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) acc = fma(__ldg(a + pk * VEC + e), r_sh[pk * VEC + e], acc);
+          for (int e = 0; e < VEC; ++e) acc = fma(a[pk * VEC + e], r_sh[pk * VEC + e], acc);
         }
       }
       for (int off = lpc >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -392,7 +383,7 @@ __device__ void ps_step_t(const PersistParams& p, const T* x, const T* g, const 
   const int packs = (ns + VEC - 1) / VEC;
   ps_block_reduce<3, 1>(acc, packs < PS_THREADS ? packs : PS_THREADS, red);
   if (threadIdx.x == 0) {
-    const bool one = gridDim.x == 1;
+    const bool one = p.shared_xchg != 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       ps_st(scal_out + 2 * k, acc.s[k].hi, one);
@@ -422,18 +413,17 @@ __device__ void ps_step(const PersistParams& p, const T* x, const T* g, const T*
 }
 
 struct PsComb {
-  double gsum, res_sq, gdr, res_inf;
+  double gsum, res_sq, gdr, res_inf, sumsq;
 };
 
 // The grid barrier and the fold of the G CTAs' reduction partials in one: warp 0 waits for the G arrival flags (lane c watches CTA c),
 // lane c then loads CTA c's partials, a fixed shuffle tree folds them, and the rounded scalars are broadcast through shared memory.
 // want_scal = false: barrier only (phases that publish just a partial product).
-__device__ PsComb ps_wait_fold(const PersistParams& p, unsigned int epoch, const double* scal, bool want_scal, double* bc) {
-  const bool one = gridDim.x == 1;
+__device__ PsComb ps_wait_fold(const PersistParams& p, unsigned int epoch, const double* scal, bool want_scal, bool one, double* bc) {
   if (threadIdx.x < 32) {
     ps_wait_warp0(p.bar, epoch);
     if (want_scal) {
-      Acc<3, 1> a;
+      Acc<4, 1> a;
       a.clear();
       if (threadIdx.x < gridDim.x) {
         const double* s = scal + (size_t)threadIdx.x * PS_SCAL;
@@ -443,13 +433,16 @@ __device__ PsComb ps_wait_fold(const PersistParams& p, unsigned int epoch, const
           a.s[k].lo = ps_ld(s + 2 * k + 1, one);
         }
         a.m[0] = ps_ld(s + 6, one);
+        a.s[3].hi = ps_ld(s + 8, one);
+        a.s[3].lo = ps_ld(s + 9, one);
       }
-      if (!one) warp_reduce<3, 1>(a);
+      if (gridDim.x > 1) warp_reduce<4, 1>(a);
       if (threadIdx.x == 0) {
         bc[0] = a.s[0].hi + a.s[0].lo;
         bc[1] = a.s[1].hi + a.s[1].lo;
         bc[2] = a.s[2].hi + a.s[2].lo;
         bc[3] = a.m[0];
+        bc[4] = a.s[3].hi + a.s[3].lo;
       }
     }
   }
@@ -459,6 +452,7 @@ __device__ PsComb ps_wait_fold(const PersistParams& p, unsigned int epoch, const
   c.res_sq = bc[1];
   c.gdr = bc[2];
   c.res_inf = bc[3];
+  c.sumsq = bc[4];
   __syncthreads();                       // everyone has read the broadcast before its next writer runs
   return c;
 }
@@ -480,6 +474,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   T* r_sh = reinterpret_cast<T*>(ps_smem) + (size_t)PS_NSLOT * p.ns_max;
   const int64_t m_pad = (p.m + 3) & ~(int64_t)3;
   T* shp = r_sh + m_pad;                              // 2048 elements: lane partials of the residual orders
+  T* dyn_next = shp + 2048;                           // one-CTA exchange buffers and / or this CTA's slice of A follow
 
   const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x;
   const int nchunk = (int)p.ord.nchunk;
@@ -492,16 +487,38 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   if (j1 < j0) j1 = j0;
   const int ns = (int)(j1 - j0);
   const int64_t m = p.m;
-  // cross-CTA buffers, double buffered by epoch parity: L2 (global) when several CTAs cooperate, shared memory when one does
-  T* partial_buf[2] = {static_cast<T*>(p.partial), static_cast<T*>(p.partial) + (size_t)nchunk * m};
+  // Cross-CTA buffers: L2 (global) when several CTAs cooperate, shared memory when one does.  Every product round is
+  // [publish chunk partials (+ the step's reduction partials)] -> barrier A -> [each CTA assembles its share of the rows of r and its
+  // share of ||r||^2] -> barrier B + fold -> [everyone copies r].  Barrier B orders the next round's writes of `partial` after this
+  // round's reads and barrier A the next writes of `r_glob` after this round's copies, so both are single buffered; the reduction
+  // partials are read after B while a fast CTA may already publish the next ones: double buffered by round parity.
+  const bool one = p.shared_xchg != 0;
+  T* partial = static_cast<T*>(p.partial);
+  T* r_glob = static_cast<T*>(p.r_glob);
   double* scal_buf[2] = {p.scal, p.scal + (size_t)PS_MAX_CTAS * PS_SCAL};
-  if (G == 1) {
-    partial_buf[0] = shp + 2048;
-    partial_buf[1] = partial_buf[0] + (size_t)nchunk * m;
+  if (one) {
+    partial = dyn_next;
+    dyn_next += (size_t)nchunk * m;
     scal_buf[0] = scal_sh;
     scal_buf[1] = scal_sh + PS_SCAL;
   }
-  unsigned int epoch = 0;
+  // this CTA's column slice of A: shared memory when it fits (read ~3 times per iteration for thousands of iterations), else L1/L2
+  const T* Aeff = static_cast<const T*>(p.A);
+  int64_t lda_eff = p.lda;
+  if (p.a_in_smem) {
+    const T* __restrict__ Ag = static_cast<const T*>(p.A);
+    T* As = dyn_next;
+    for (int64_t idx = tid; idx < (int64_t)ns * m; idx += PS_THREADS) {
+      const int64_t jj = idx / m, ii = idx - jj * m;
+      As[idx] = __ldg(Ag + ii + (j0 + jj) * p.lda);
+    }
+    Aeff = As - j0 * m;
+    lda_eff = m;
+  }
+  const int64_t rows_base = m / G, rows_extra = m % G;
+  const int64_t i0 = cta * rows_base + (cta < rows_extra ? cta : rows_extra);
+  const int64_t i1 = i0 + rows_base + (cta < rows_extra ? 1 : 0);
+  unsigned int epoch = 0, gen = 0;
   long long t_last = 0;
   if (p.timing && cta == 0 && tid == 0) {
     for (int k = 0; k < PS_NPHASE; ++k) cyc[k] = 0;
@@ -527,31 +544,61 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
 
   auto publish_Av = [&](const T* v) {          // chunk partials of A v into the buffer of the NEXT barrier
     lap(PS_PH_OTHER);
-    T* part = partial_buf[(epoch + 1) & 1];
     if (p.ord.n_sub)
-      ps_gemv_n_sub<T>(p, v, j0, ch0, ch1, part, shp);
+      ps_gemv_n_sub<T>(p, Aeff, lda_eff, v, j0, ch0, ch1, partial, shp, one);
     else
-      ps_gemv_n_rows<T>(p, v, j0, ch0, ch1, part, shp);
+      ps_gemv_n_rows<T>(p, Aeff, lda_eff, v, j0, ch0, ch1, partial, shp, one);
     lap(PS_PH_GEMV_N);
   };
-  auto scal_slot = [&]() { return scal_buf[(epoch + 1) & 1] + (size_t)cta * PS_SCAL; };
-  // grid barrier (+ fold of the reduction partials published for it)
+  auto scal_slot = [&]() { return scal_buf[gen & 1] + (size_t)cta * PS_SCAL; };
+  // grid barrier (+ fold of the reduction partials of the current round)
   auto sync_fold = [&](bool want_scal) {
     lap(PS_PH_OTHER);
     epoch += 1;
     ps_arrive(p.bar, epoch);
-    const PsComb c = ps_wait_fold(p, epoch, scal_buf[epoch & 1], want_scal, bc);
+    const PsComb c = ps_wait_fold(p, epoch, scal_buf[gen & 1], want_scal, one, bc);
     lap(PS_PH_BARRIER);
     return c;
   };
-  auto combine = [&]() {
-    const double a = ps_combine_r<T>(p, partial_buf[epoch & 1], r_sh, bc, red);
-    lap(PS_PH_COMBINE);
-    return a;
+  // Completes a product round started by publish_Av (the step's reduction partials, if any, are already in this round's slots):
+  // leaves r = A v - b in shared memory, returns ||r||^2 and (with_scal) the folded reductions of the step.
+  auto round_Av = [&](bool with_scal, PsComb& sc_out) {
+    double aux_out;
+    Acc<1, 1> a;
+    if (G == 1) {
+      __syncthreads();
+      ps_combine_rows<T>(p, partial, r_sh, true, 0, m, one, a, red);
+      if (tid == 0) {
+        double* so = scal_slot();
+        ps_st(so + 8, a.s[0].hi, one);
+        ps_st(so + 9, a.s[0].lo, one);
+      }
+      lap(PS_PH_COMBINE);
+      const PsComb c = sync_fold(true);
+      if (with_scal) sc_out = c;
+      aux_out = c.sumsq;
+    } else {
+      (void)sync_fold(false);                    // barrier A: every chunk partial is in L2
+      ps_combine_rows<T>(p, partial, r_glob, false, i0, i1, false, a, red);
+      if (tid == 0) {
+        double* so = scal_slot();
+        __stcg(so + 8, a.s[0].hi);
+        __stcg(so + 9, a.s[0].lo);
+      }
+      lap(PS_PH_COMBINE);
+      const PsComb c = sync_fold(true);          // barrier B: every row share of r is in L2
+      if (with_scal) sc_out = c;
+      aux_out = c.sumsq;
+      for (int64_t i = tid; i < m; i += PS_THREADS) r_sh[i] = __ldcg(r_glob + i);
+      __syncthreads();
+      lap(PS_PH_COMBINE);
+    }
+    gen += 1;
+    return aux_out;
   };
   auto gemv_t = [&](T* gout) {
     lap(PS_PH_OTHER);
-    ps_gemv_t<T>(p, r_sh, gout, j0, j1);
+    ps_gemv_t<T>(p, Aeff, lda_eff, r_sh, gout, j0, j1);
     __syncthreads();
     lap(PS_PH_GEMV_T);
   };
@@ -568,15 +615,14 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   const bool adaptive = p.adaptive != 0;
   const R min_gamma = (R)p.minimum_gamma, red_gamma = (R)p.reduce_gamma, inc_gamma = (R)p.increase_gamma;
   R gamma, f_x = R(0), g_z = R(0);
-  PsComb sc;
   double aux, aux_n;
   int64_t backtracks = 0;
   int warned = 0;
 
   // ---- init: forward_backward.jl:65-84 / fast_forward_backward.jl:73-97 ----
+  PsComb sc, sc_dummy;
   publish_Av(X);
-  (void)sync_fold(false);
-  aux = combine();                              // r = A x - b
+  aux = round_Av(false, sc_dummy);              // r = A x - b
   gemv_t(GR);                                   // grad f(x)
   bool fx_pending = true;
   if (p.gamma <= 0) {                           // fb_tools.jl:7-12 with A = I
@@ -585,8 +631,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
     for (int e = tid; e < ns; e += PS_THREADS) W2[e] = add_rn(X[e], T(1));
     __syncthreads();
     publish_Av(W2);
-    (void)sync_fold(false);
-    (void)combine();
+    (void)round_Av(false, sc_dummy);
     gemv_t(Z);                                  // z is free at this point: holds grad f(x + 1)
     Acc<1, 1> a;
     a.clear();
@@ -601,11 +646,12 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
     ps_block_reduce<1, 1>(a, ns < PS_THREADS ? ns : PS_THREADS, red);
     if (tid == 0) {
       double* so = scal_slot();
-      ps_st(so + 0, a.s[0].hi, G == 1);
-      ps_st(so + 1, a.s[0].lo, G == 1);
-      for (int k = 2; k < 7; ++k) ps_st(so + k, 0.0, G == 1);
+      ps_st(so + 0, a.s[0].hi, one);
+      ps_st(so + 1, a.s[0].lo, one);
+      for (int k = 2; k < 10; ++k) ps_st(so + k, 0.0, one);
     }
     const PsComb c2 = sync_fold(true);
+    gen += 1;
     const int64_t n_glob = p.n_global > 0 ? p.n_global : p.n;
     const R lower = (R)sqrt(c2.gsum) / (R)sqrt((double)n_glob);
     gamma = R(1) / lower;
@@ -623,9 +669,8 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
   const bool fused_extrap = fast && !adaptive;
   if (fused_extrap) beta_next = seq.next(gamma);
   step(X, GR, ZP, gamma, beta_next, fused_extrap, Z, W1);
-  publish_Av(fused_extrap ? W1 : Z);            // the product the next operation needs rides on the same barrier
-  sc = sync_fold(true);
-  aux_n = combine();
+  publish_Av(fused_extrap ? W1 : Z);            // the product the next operation needs rides on the same barriers
+  aux_n = round_Av(true, sc);
   if (fx_pending) f_x = f_value(aux);
   g_z = g_value(sc);
 
@@ -640,8 +685,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
       gamma = gamma * red_gamma;
       step(X, GR, ZP, gamma, R(0), false, Z, W1);
       publish_Av(Z);
-      sc = sync_fold(true);
-      aux_n = combine();
+      aux_n = round_Av(true, sc);
       g_z = g_value(sc);
       f_upp = pb_f_model<R>(f_x, sc.gdr, sc.res_sq, R(1) / gamma);
       if (want_grad) gemv_t(W1);
@@ -673,8 +717,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
       }
       step(X, GR, ZP, gamma, R(0), false, Z, W1);
       publish_Av(Z);
-      sc = sync_fold(true);
-      aux_n = combine();
+      aux_n = round_Av(true, sc);
       if (!adaptive) f_x = f_value(aux);
       g_z = g_value(sc);
     } else {                                      // fast_forward_backward.jl:106-145
@@ -687,8 +730,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
         T* t = ZP; ZP = Z; Z = t;                 // :136
         __syncthreads();
         publish_Av(X);
-        (void)sync_fold(false);
-        aux = combine();
+        aux = round_Av(false, sc_dummy);
         gemv_t(GR);
         step(X, GR, ZP, gamma, R(0), false, Z, W1);
         publish_Av(Z);
@@ -702,8 +744,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
         step(X, GR, ZP, gamma, beta_next, true, Z, W1);
         publish_Av(W1);
       }
-      sc = sync_fold(true);
-      aux_n = combine();
+      aux_n = round_Av(true, sc);
       f_x = f_value(aux);
       g_z = g_value(sc);
     }
@@ -747,6 +788,7 @@ __global__ void __launch_bounds__(PS_THREADS, 1) k_persist_solve(PersistParams p
 struct PersistPlan {
   int ctas;
   int ns_max;
+  int shared_xchg, a_in_smem;
   size_t smem;
   PbLsqOrder ord;
 };
@@ -766,9 +808,21 @@ static bool persist_plan(const pb_ctx* ctx, const pb_smooth* f, int want_ctas, P
   if (G < 1) G = 1;
   const int64_t ns_max = ((int64_t)(nchunk + G - 1) / G) * plan->ord.chunk_cols;
   const int64_t m_pad = (m + 3) & ~(int64_t)3;
-  // one CTA: the chunk partials [2][nchunk][m] live in shared memory too (no trip through L2)
-  const size_t smem = ((size_t)PS_NSLOT * ns_max + m_pad + 2048 + (G == 1 ? (size_t)2 * nchunk * m : 0)) * sizeof(T);
-  if (smem > 200 * 1024) return false;
+  const size_t limit = 200 * 1024;
+  size_t smem = ((size_t)PS_NSLOT * ns_max + m_pad + 2048) * sizeof(T);
+  if (smem > limit) return false;
+  // one CTA: the chunk partials [nchunk][m] live in shared memory too (no trip through L2)
+  plan->shared_xchg = 0;
+  if (G == 1 && smem + (size_t)nchunk * m * sizeof(T) <= limit) {
+    plan->shared_xchg = 1;
+    smem += (size_t)nchunk * m * sizeof(T);
+  }
+  // the CTA's column slice of A in shared memory when it fits
+  plan->a_in_smem = 0;
+  if (smem + (size_t)ns_max * m * sizeof(T) <= limit) {
+    plan->a_in_smem = 1;
+    smem += (size_t)ns_max * m * sizeof(T);
+  }
   plan->ctas = G;
   plan->ns_max = (int)ns_max;
   plan->smem = smem;
@@ -794,8 +848,9 @@ static int persist_run(pb_ctx* ctx, int64_t n, const pb_smooth* f, const pb_prox
   }
   PB_CHECK_CUDA(cudaSetDevice(ctx->device));
   // workspace: [2][nchunk][m] chunk partials + [2][32][8] reduction partials + barrier counter + result
-  const size_t part_bytes = (size_t)2 * plan.ord.nchunk * f->m * sizeof(T);
-  const size_t scal_off = (part_bytes + 255) & ~(size_t)255;
+  const size_t part_bytes = (size_t)plan.ord.nchunk * f->m * sizeof(T);
+  const size_t rglob_off = (part_bytes + 255) & ~(size_t)255;
+  const size_t scal_off = (rglob_off + (size_t)f->m * sizeof(T) + 255) & ~(size_t)255;
   const size_t scal_bytes = (size_t)2 * PS_MAX_CTAS * PS_SCAL * sizeof(double);
   const size_t bar_off = scal_off + scal_bytes;
   const size_t res_off = bar_off + (size_t)PS_MAX_CTAS * PS_FLAG_STRIDE * sizeof(unsigned int);
@@ -835,6 +890,9 @@ static int persist_run(pb_ctx* ctx, int64_t n, const pb_smooth* f, const pb_prox
   p.increase_gamma = o->increase_gamma;
   p.ord = plan.ord;
   p.partial = ws;
+  p.r_glob = ws + rglob_off;
+  p.shared_xchg = plan.shared_xchg;
+  p.a_in_smem = plan.a_in_smem;
   p.scal = reinterpret_cast<double*>(ws + scal_off);
   p.bar = reinterpret_cast<unsigned int*>(ws + bar_off);
   p.ns_max = plan.ns_max;

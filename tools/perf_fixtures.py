@@ -52,6 +52,8 @@ def main():
             "DouglasRachford": (lambda: po.douglas_rachford(x0, f=fo_px, g=go, gamma=1.0, tol=1e-6), lambda s: s(x0=x0, f=fg, g=gg, gamma=1.0),
                                 lambda: pa.DouglasRachford(tol=1e-6)),
         }
+        if "--fb-only" in sys.argv:
+            cases = {k: v for k, v in cases.items() if k.endswith("ForwardBackward")}
         for alg, (f_cpu, f_gpu, mk) in cases.items():
             (_, it_c), t_c = best_of(f_cpu)
             row = {"oracle_iterations": int(it_c), "oracle_seconds": t_c, "oracle_it_per_s": it_c / t_c}
