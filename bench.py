@@ -263,6 +263,7 @@ def run_b200(args):
 
     K = args.steps
     sampler = None
+    multi_iter = False
     if args.loop == "native":
         # The product's own driver loop (pb_solve, csrc/solve.cu) through the public solver API, on device-resident tensors:
         # f = <c, x> makes c the "supplied gradient buffer", beta = 0.5 is a constant extrapolation sequence, tol < 0 never
@@ -289,6 +290,7 @@ def run_b200(args):
         last_res_inf = float(solver.last_state.res_norm_inf)
         parity = dict(solver.last_parity)
         parity["g_z"] = float(solver.last_state.g_z)
+        multi_iter = bool(getattr(solver, "last_multi_iter_kernel", False))
         del zsol
     else:
         for _ in range(max(3, args.warmup)):
@@ -411,10 +413,14 @@ def run_b200(args):
             "config": {"workload": "M3 Lasso FISTA fused-step-only: n=1e8 fp32 total, NormL1(1), gamma=0.1, beta=0.5, gradient supplied as a resident buffer; "
                                    "step = one iteration of the inner loop = pb_ffb_step (K2) + per-iteration scalar exchange + host stop test" +
                                    (", driven by the library's loop pb_solve via pa.FastForwardBackward(maxit=K, tol<0, driver=native)" if args.loop == "native" else ", driven by a Python loop in bench.py"),
-                       "loop": args.loop,
+                       "loop": args.loop, "iterations_in_one_persistent_kernel": multi_iter,
                        "n": args.n, "n_per_gpu": n, "parallelism": f"row-shard x{world}", "exchange": args.exchange, "l2": "inputs exceed L2 (5 x %.0f MB streams per GPU)" % (4 * n / 1e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(n), "kernel": "k_step<float, L1, EXTRAP> (pb_ffb_step)", "kernel_ms": kern_ms_max,
+                         "traffic": ncu_traffic(n),
+                         "kernel": ("k_step_multi<float, L1> (csrc/step_multi.cu: ONE persistent launch loops over the K iterations; kernel_ms = its "
+                                    "CUDA-event duration / K, i.e. per iteration including the in-kernel fold, exchange and stop test)") if multi_iter
+                                   else "k_step<float, L1, EXTRAP> (pb_ffb_step)",
+                         "kernel_ms": kern_ms_max,
                          "algorithmic_bytes_per_launch": BYTES_PER_ELT * n, "peak_source": peak_src,
                          "note": ("kernel_ms = CUDA-event duration of the K2 launches inside the timed region. --loop native with the device exchange "
                                   "runs the pipelined driver (pb_solve look-ahead): K2 writes per-CTA partials and a 1-CTA kernel on a side stream "

@@ -117,6 +117,9 @@ enum {
                                shared-memory ring                                                                 */
   PB_OPT_FUSED_EXCHANGE = 4,/* 1: pb_fb_step / pb_ffb_step also perform the per-iteration exchange (pb_xchg_*) in their
                                last CTA, so the iteration needs no collective launch, memcpy or stream sync       */
+  PB_OPT_MULTI_ITER = 6,    /* pb_solve, fixed-stepsize FFB with an element-wise gradient source (LinearFunction, SquaredDistance):
+                               0 = auto (ONE persistent kernel loops over the iterations, csrc/step_multi.cu; off when contexts
+                               of one process share a GPU), -1 = never (one launch per iteration), 1 = always.  Same results */
   PB_OPT_PERSISTENT = 5     /* pb_solve on cache-resident dense least squares (m*n*sizeof <= 8 MB): 0 = auto (whole solve
                                in one persistent cooperative kernel, csrc/persist.cu), -1 = never (one kernel per
                                operation), 1..32 = persistent on at most that many CTAs.  Results do not depend on it */
@@ -329,6 +332,9 @@ typedef struct pb_solve_result {
    * dot(grad_f_x, res) (the f_model terms, fb_tools.jl:3-5) and sum|z| (L1) / sum_g scal_g*||y_g|| (L21).  Identical
    * for every sharding of the iterate -- bench.py prints them as its cross-N parity fingerprint. */
   double res_sq, gdr, gsum;
+  int32_t multi_iter_kernel;    /* 1: the iterations ran inside ONE persistent kernel (csrc/step_multi.cu); step_kernel_launches
+                                   then counts iterations and step_kernel_ms is that kernel's duration                        */
+  int32_t pad;
 } pb_solve_result;
 
 /* x holds copy(x0) on entry.  grad, z, scratch: n-vectors.  z_prev, x_next: FFB only.  grad_z: adaptive FB only. */

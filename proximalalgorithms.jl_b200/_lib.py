@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libproxb200.so")
 
 PB_F32, PB_F64 = 0, 1
 PB_PROX_ZERO, PB_PROX_L1, PB_PROX_BOX, PB_PROX_SCALE, PB_PROX_L21, PB_PROX_SQRL2 = 0, 1, 2, 3, 4, 5
-PB_OPT_CTAS_PER_SM, PB_OPT_STREAM_HINTS, PB_OPT_UNROLL, PB_OPT_STEP_IMPL, PB_OPT_FUSED_EXCHANGE, PB_OPT_PERSISTENT = 0, 1, 2, 3, 4, 5
+PB_OPT_CTAS_PER_SM, PB_OPT_STREAM_HINTS, PB_OPT_UNROLL, PB_OPT_STEP_IMPL, PB_OPT_FUSED_EXCHANGE, PB_OPT_PERSISTENT, PB_OPT_MULTI_ITER = 0, 1, 2, 3, 4, 5, 6
 PB_IPC_HANDLE_BYTES, PB_MAX_WORLD = 64, 8
 PB_S_GSUM, PB_S_RESSQ, PB_S_GDR, PB_S_RESINF, PB_S_AUX, PB_S_AUXINF, PB_S_AUX2, PB_S_AUX3, PB_NSCALARS = 0, 2, 4, 6, 8, 10, 12, 14, 16
 
@@ -49,7 +49,8 @@ class pb_solve_result(C.Structure):
     _fields_ = [("iterations", C.c_int64), ("backtracks", C.c_int64), ("gamma", C.c_double), ("f_x", C.c_double), ("g_z", C.c_double),
                 ("res_inf", C.c_double), ("warned_small_gamma", C.c_int32), ("persistent_ctas", C.c_int32), ("x", C.c_void_p), ("grad", C.c_void_p),
                 ("z", C.c_void_p), ("z_prev", C.c_void_p), ("loop_ms", C.c_double), ("step_kernel_ms", C.c_double),
-                ("step_kernel_launches", C.c_int64), ("res_sq", C.c_double), ("gdr", C.c_double), ("gsum", C.c_double)]
+                ("step_kernel_launches", C.c_int64), ("res_sq", C.c_double), ("gdr", C.c_double), ("gsum", C.c_double),
+                ("multi_iter_kernel", C.c_int32), ("pad", C.c_int32)]
 
 
 class pb_panoc_opts(C.Structure):

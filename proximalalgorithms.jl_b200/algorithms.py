@@ -545,6 +545,7 @@ def _native_solve(alg, it):
     st._sc = _Sc
     it.backtracks = int(res.backtracks)
     alg.last_persistent_ctas = int(res.persistent_ctas)     # > 0: the whole solve was ONE persistent kernel (csrc/persist.cu)
+    alg.last_multi_iter_kernel = bool(res.multi_iter_kernel)   # the iterations ran inside one persistent step kernel (csrc/step_multi.cu)
     alg.last_parity = {"res_inf": float(res.res_inf), "res_sq": float(res.res_sq), "gdr": float(res.gdr), "gsum": float(res.gsum)}
     alg.last_iteration, alg.last_state = it, st
     sol = _like_input(it.x0, st.z)

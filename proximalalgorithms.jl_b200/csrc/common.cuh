@@ -41,6 +41,8 @@ struct pb_ctx {
   int step_impl;       // 0 = default, 1 = register pipeline, 2 = TMA bulk ring
   int persist_mode;    // PB_OPT_PERSISTENT: 0 auto, -1 never, k > 0 at most k CTAs
   long long persist_cycles[8];   // per-phase clock64() totals of the last profiled persistent solve
+  int multi_mode;      // PB_OPT_MULTI_ITER: 0 auto, -1 never, 1 force (even when contexts share a device)
+  void* multi_ws;      // workspace of the persistent multi-iteration step kernel (step_multi.cu)
   double* scalars_dev;   // active scalar block (own or caller supplied)
   double* scalars_own;
   double* scalars_host;  // pinned mirror
@@ -61,6 +63,8 @@ struct pb_ctx {
   int xchg_rank, xchg_world;                // world == 0: not initialised
   int xchg_connected;
   int xchg_local;                           // peers are contexts of this process (pb_xchg_connect_local): nothing to cudaIpcClose
+  int xchg_shared_device;                   // some peer context lives on the same GPU: kernels that need the whole GPU to be
+                                            // co-resident while they wait for a peer (step_multi.cu) are not used
   int xchg_fused;                           // K1/K2 push in-kernel
   int xchg_pending;                         // a launched kernel will publish xchg_seq
   int64_t xchg_pending_launch;              // value of `launches` right after that kernel's launch

@@ -93,6 +93,7 @@ extern "C" int pb_ctx_destroy(pb_ctx* c) {
   for (int k = 0; k < 5; ++k)
     if (c->hbuf[k]) cudaFree(c->hbuf[k]);
   if (c->scratch) cudaFree(c->scratch);
+  if (c->multi_ws) cudaFree(c->multi_ws);
   if (c->ws) cudaFree(c->ws);
   if (c->side_stream) {
     cudaStreamSynchronize(c->side_stream);
@@ -148,6 +149,10 @@ extern "C" int pb_ctx_set_option(pb_ctx* c, int option, int value) {
     case PB_OPT_PERSISTENT:
       PB_REQUIRE(value >= -1 && value <= 32, "persistent mode must be -1, 0 or 1..32");
       c->persist_mode = value;
+      return PB_OK;
+    case PB_OPT_MULTI_ITER:
+      PB_REQUIRE(value >= -1 && value <= 1, "multi-iteration mode must be -1, 0 or 1");
+      c->multi_mode = value;
       return PB_OK;
     case PB_OPT_FUSED_EXCHANGE:
       PB_REQUIRE(value == 0 || value == 1, "fused exchange must be 0 or 1");

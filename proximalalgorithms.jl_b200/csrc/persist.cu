@@ -71,8 +71,7 @@ enum { PS_PH_GEMV_N = 0, PS_PH_BARRIER, PS_PH_COMBINE, PS_PH_GEMV_T, PS_PH_STEP,
 // lane c of warp 0 polls CTA c's flag (acquire), so the G flags are watched in parallel and nothing serialises on one address.
 __device__ __forceinline__ void ps_arrive(unsigned int* bar, unsigned int epoch) {
   __syncthreads();                       // this CTA's partials are written
-  if (gridDim.x > 1 && threadIdx.x == 0) {
-    __threadfence();
+  if (gridDim.x > 1 && threadIdx.x == 0) {   // release is cumulative: it also orders the other threads' writes seen through bar.sync
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + (size_t)blockIdx.x * PS_FLAG_STRIDE), "r"(epoch) : "memory");
   }
 }
@@ -100,6 +99,24 @@ __device__ __forceinline__ T ps_ld(const T* p, bool one) {
   return one ? *p : __ldcg(p);
 }
 
+// warp_reduce of common.cuh with the level loop ROLLED: each double-double level is ~100 instructions per sum, and the fully unrolled
+// trees made every phase routine 20-40 KB of SASS (instruction-cache misses dominated the small problems)
+template <int NSUM, int NMAX>
+__device__ __forceinline__ void ps_warp_reduce(Acc<NSUM, NMAX>& a) {
+#pragma unroll 1
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NSUM; ++k) {
+      dd o;
+      o.hi = shfl_down_d(a.s[k].hi, off);
+      o.lo = shfl_down_d(a.s[k].lo, off);
+      a.s[k] = dd_sum(a.s[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) a.m[k] = nanmax(a.m[k], shfl_down_d(a.m[k], off));
+  }
+}
+
 // Block reduction restricted to the warps that hold data (`active` threads, tid < active): the double-double shuffle trees are
 // FP64-pipe bound, and a slice of 32 columns keeps 8 of the 512 threads busy.  Result valid in thread 0; `red`: 16 x 8 doubles.
 template <int NSUM, int NMAX>
@@ -108,7 +125,7 @@ __device__ __forceinline__ void ps_block_reduce(Acc<NSUM, NMAX>& a, int active, 
   int naw = (active + 31) >> 5;
   if (naw < 1) naw = 1;
   if (warp < naw) {
-    warp_reduce<NSUM, NMAX>(a);
+    ps_warp_reduce<NSUM, NMAX>(a);
     if (lane == 0 && naw > 1) {
 #pragma unroll
       for (int k = 0; k < NSUM; ++k) {
@@ -129,17 +146,19 @@ __device__ __forceinline__ void ps_block_reduce(Acc<NSUM, NMAX>& a, int active, 
       }
 #pragma unroll
       for (int k = 0; k < NMAX; ++k) a.m[k] = lane < naw ? red[lane * 8 + 6 + k] : 0.0;
-      warp_reduce<NSUM, NMAX>(a);
+      ps_warp_reduce<NSUM, NMAX>(a);
     }
   }
 }
 
+// The phase routines below are __noinline__ on purpose: the driver loop calls them from many places, and fully inlined the kernel
+// was ~1 MB of SASS -- every iteration then ran out of the instruction cache (measured: 1-2k cycles of fetch stalls per phase).
 // ---------------------------------------------------------------------------------------------------------------------
 // r = A v - b, phase 1: partial[ch][i] = sum_{j in chunk ch} A[i, j] v[j] for the chunks this CTA owns.  v: shared-memory slice,
 // element j lives at v[j - j0].  Two summation orders, exactly those of k_gemv_n_partial / k_gemv_n_sub (lsq_kernels.cu).
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ v, int64_t j0, int ch0,
+__device__ __noinline__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ v, int64_t j0, int ch0,
                                int ch1, T* partial, T* shp, bool one) {
   // row-per-thread order: 4 column lanes, each a sequential FMA chain over its columns j = c0 + cl, c0 + cl + 4, ...; the
   // lanes are then added ((l0 + l1) + l2) + l3.  512 threads = 128 rows x 4 lanes, four row tiles in flight per thread.
@@ -192,7 +211,7 @@ __device__ void ps_gemv_n_rows(const PersistParams& p, const T* __restrict__ A, 
 }
 
 template <typename T>
-__device__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ v, int64_t j0, int ch0,
+__device__ __noinline__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ v, int64_t j0, int ch0,
                               int ch1, T* partial, T* shp, bool one) {
   // short-column order (m < 64): LPC lanes share a column, each owning up to KP 16-byte packs of it; a "virtual CTA" of 256
   // threads (8 warps) works one chunk exactly like k_gemv_n_sub does, two virtual CTAs side by side.
@@ -262,7 +281,7 @@ __device__ void ps_gemv_n_sub(const PersistParams& p, const T* __restrict__ A, i
 // `acc`.  One CTA: all rows, r into shared memory.  Several CTAs: each assembles ITS share of the rows (the partials of all chunks
 // of a row are 8-byte loads from L2) and publishes it; after a second barrier everyone copies the m values of r.
 template <typename T>
-__device__ void ps_combine_rows(const PersistParams& p, const T* partial, T* r_out, bool r_shared, int64_t i0, int64_t i1, bool one,
+__device__ __noinline__ void ps_combine_rows(const PersistParams& p, const T* partial, T* r_out, bool r_shared, int64_t i0, int64_t i1, bool one,
                                 Acc<1, 1>& acc, double* red) {
   constexpr bool COMP = sizeof(T) == 8;
   const T* __restrict__ b = static_cast<const T*>(p.b);
@@ -293,7 +312,7 @@ __device__ void ps_combine_rows(const PersistParams& p, const T* partial, T* r_o
 
 // grad_j = sum_i A[i, j] r_i for this CTA's columns, in the order of k_gemv_t (warp per column) or k_gemv_t_sub (LPC lanes per column)
 template <typename T>
-__device__ void ps_gemv_t(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ r_sh, T* g, int64_t j0, int64_t j1) {
+__device__ __noinline__ void ps_gemv_t(const PersistParams& p, const T* __restrict__ A, int64_t lda, const T* __restrict__ r_sh, T* g, int64_t j0, int64_t j1) {
   constexpr int VEC = 16 / sizeof(T);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t m = p.m;
@@ -341,7 +360,7 @@ __device__ void ps_gemv_t(const PersistParams& p, const T* __restrict__ A, int64
 // the fused forward-backward step on this CTA's slice (same StepElem arithmetic as K1/K2) + publication of its reduction partials
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T, int PROX, bool EXTRAP>
-__device__ void ps_step_t(const PersistParams& p, const T* x, const T* g, const T* zp, T gamma, T beta, T* z, T* xn, int64_t j0,
+__device__ __noinline__ void ps_step_t(const PersistParams& p, const T* x, const T* g, const T* zp, T gamma, T beta, T* z, T* xn, int64_t j0,
                           int ns, double* scal_out, double* red) {
   constexpr bool COMP = sizeof(T) == 8;
   const T* __restrict__ lov = static_cast<const T*>(p.lo_v);
@@ -419,7 +438,7 @@ struct PsComb {
 // The grid barrier and the fold of the G CTAs' reduction partials in one: warp 0 waits for the G arrival flags (lane c watches CTA c),
 // lane c then loads CTA c's partials, a fixed shuffle tree folds them, and the rounded scalars are broadcast through shared memory.
 // want_scal = false: barrier only (phases that publish just a partial product).
-__device__ PsComb ps_wait_fold(const PersistParams& p, unsigned int epoch, const double* scal, bool want_scal, bool one, double* bc) {
+__device__ __noinline__ PsComb ps_wait_fold(const PersistParams& p, unsigned int epoch, const double* scal, bool want_scal, bool one, double* bc) {
   if (threadIdx.x < 32) {
     ps_wait_warp0(p.bar, epoch);
     if (want_scal) {
@@ -436,7 +455,7 @@ __device__ PsComb ps_wait_fold(const PersistParams& p, unsigned int epoch, const
         a.s[3].hi = ps_ld(s + 8, one);
         a.s[3].lo = ps_ld(s + 9, one);
       }
-      if (gridDim.x > 1) warp_reduce<4, 1>(a);
+      if (gridDim.x > 1) ps_warp_reduce<4, 1>(a);
       if (threadIdx.x == 0) {
         bc[0] = a.s[0].hi + a.s[0].lo;
         bc[1] = a.s[1].hi + a.s[1].lo;

@@ -17,6 +17,9 @@
 #include "common.cuh"
 #include "solve_scalar.h"
 
+bool pb_multi_eligible(const pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o, const void* x_next);   // step_multi.cu
+int pb_multi_run(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o, void* const X[3],
+                 void* const Z[3], int64_t* k_out, double comb[4], float* kernel_ms);
 bool pb_persist_eligible(const pb_ctx* ctx, int dtype, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o);   // persist.cu
 int pb_persist_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o, void* x,
                      void* grad, void* z, void* z_prev, pb_solve_result* out);
@@ -277,6 +280,11 @@ struct Solver {
     Nesterov<R> seq;
     seq.init(o->sequence, (R)o->mf, (R)o->constant_beta);
     R beta_next = R(0);
+    // element-wise gradient source + fixed stepsize: one persistent kernel loops over the iterations (step_multi.cu), same results
+    if (fast && !adaptive && pb_multi_eligible(ctx, dtype, n, f, g, o, x_next)) {
+      rc = run_ffb_multi(out);
+      if (rc != PB_EUNSUPPORTED) return rc;
+    }
     if (fast) {
       if ((rc = pb_copy(ctx, z_prev, x, (size_t)n * (dtype == PB_F32 ? 4 : 8)))) return rc;     // z_prev = copy(x)
       if (!adaptive) {
@@ -407,6 +415,45 @@ struct Solver {
   }
 
   int eval_f_to(const void* v, void* grad_out) { return eval_f(v, grad_out); }
+
+  // Fixed-stepsize FFB, f = <c, .> or SquaredDistance: iterations 1 .. k inside ONE kernel (csrc/step_multi.cu).  The rings are laid
+  // out so that iteration 1 reads the caller's x (= copy(x0)) and z_prev (= copy(x)): X[1] = x, Z[0] = z_prev.
+  int run_ffb_multi(pb_solve_result* out) {
+    int rc;
+    if ((rc = pb_copy(ctx, z_prev, x, (size_t)n * (dtype == PB_F32 ? 4 : 8)))) return rc;     // z_prev = copy(x)
+    void* X[3] = {o->spare_x, x, x_next};
+    void* Z[3] = {z_prev, z, o->spare_z};
+    int64_t k = 0;
+    double comb[4];
+    float ms = 0.f;
+    rc = pb_multi_run(ctx, dtype, n, f, g, o, X, Z, &k, comb, profile ? &ms : nullptr);
+    if (rc != PB_OK) return rc;
+    x = X[k % 3];
+    x_next = X[(k + 1) % 3];
+    z = Z[k % 3];
+    z_prev = Z[(k + 2) % 3];
+    sc.gsum = comb[0];
+    sc.res_sq = comb[1];
+    sc.gdr = comb[2];
+    sc.res_inf = comb[3];
+    sc.aux = sc.local_aux = 0.0;
+    g_z = g_value(sc);
+    if (f->kind == PB_F_SQDIST) {          // grad f and f of the final state (the loop itself never consumes f with a fixed stepsize)
+      if ((rc = eval_f(x, grad))) return rc;
+      Comb c;
+      if ((rc = read_comb(ctx, &c))) return rc;
+      f_x = f_value(c);
+    }
+    rc = finish(out, k);                   // LinearFunction: f(x) = <c, x> of the final state (lazy_value)
+    out->multi_iter_kernel = 1;
+    if (profile) {
+      out->loop_ms = ms;
+      out->step_kernel_ms = ms;
+      out->step_kernel_launches = k;       // the one launch covers k iterations: step_kernel_ms / launches = time per iteration
+      profile = false;                     // run() must not overwrite these with its own events
+    }
+    return rc;
+  }
 
   int finish(pb_solve_result* out, int64_t k) {
     int rc;

@@ -104,6 +104,8 @@ extern "C" int pb_xchg_connect_local(pb_ctx** ctxs, int n) {
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PB_CHECK_CUDA(e);
         cudaGetLastError();
       }
+      else if (q != r)
+        ctxs[r]->xchg_shared_device = 1;
       ctxs[r]->xchg_peer[q] = ctxs[q]->xchg_own;
     }
     ctxs[r]->xchg_connected = 1;
@@ -125,6 +127,7 @@ extern "C" int pb_xchg_shutdown(pb_ctx* ctx) {
   ctx->xchg_world = 0;
   ctx->xchg_connected = 0;
   ctx->xchg_local = 0;
+  ctx->xchg_shared_device = 0;
   ctx->xchg_fused = 0;
   ctx->xchg_pending = 0;
   return PB_OK;

@@ -82,3 +82,36 @@ __device__ __forceinline__ void xchg_push_wait(const XchgParams& xp, const doubl
   //    while the kernel of exchange k+1 -- launched ahead by the pipelined driver loop -- publishes)
   st_word(xp.host_words + (size_t)par * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW + t, v);
 }
+
+// Variant for kernels that consume the rows themselves (the persistent multi-iteration step kernel, step_multi.cu): same push / poll
+// protocol, but the P rows are decoded into shared memory (`rows_sh`: world x PB_NSCALARS doubles, rank order) instead of being
+// forwarded to the host.  Executed by ALL threads of one CTA (blockDim.x >= world * 32); returns false if a peer timed out.
+__device__ __forceinline__ bool xchg_push_gather(const XchgParams& xp, const double* local_block, double* rows_sh) {
+  const int t = threadIdx.x;
+  const int par = (int)(xp.seq & 1u);
+  const int nwords = xp.world * PB_XCHG_WORDS_PER_ROW;
+  int bad = 0;
+  if (t < nwords) {
+    const int r = t / PB_XCHG_WORDS_PER_ROW, w = t % PB_XCHG_WORDS_PER_ROW;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(local_block[w >> 1]);
+    const unsigned int half = (w & 1) ? (unsigned int)(bits >> 32) : (unsigned int)(bits & 0xffffffffull);
+    const unsigned long long word = ((unsigned long long)xp.seq << 32) | half;
+    unsigned long long v = word;
+    if (r != xp.rank) {
+      st_word(xp.peer[r] + ((size_t)(par * PB_MAX_RANKS + xp.rank) * PB_XCHG_WORDS_PER_ROW + w), word);
+      const unsigned long long* mine = xp.peer[xp.rank] + ((size_t)(par * PB_MAX_RANKS + r) * PB_XCHG_WORDS_PER_ROW + w);
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned int spins = 0;
+      v = ld_word(mine);
+      while ((unsigned int)(v >> 32) != xp.seq) {
+        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > PB_XCHG_TIMEOUT_NS) {
+          bad = 1;
+          break;
+        }
+        v = ld_word(mine);
+      }
+    }
+    reinterpret_cast<unsigned int*>(rows_sh)[r * PB_XCHG_WORDS_PER_ROW + w] = (unsigned int)(v & 0xffffffffull);
+  }
+  return __syncthreads_or(bad) == 0;
+}
