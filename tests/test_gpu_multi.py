@@ -62,6 +62,7 @@ def test_one_kernel_for_all_iterations_same_bits(T, n):
         (dict(x0=xs, f=pa.SquaredDistance(b), g=pa.NormL1(T(0.3)), gamma=T(0.7)), T(-1), 3),
     ]
     ctx = Context.get()
+    stopped = []
     for kw, tol, maxit in cases:
         ref = _run(-1, tol, maxit, **kw)
         l0 = ctx.launches()
@@ -74,8 +75,8 @@ def test_one_kernel_for_all_iterations_same_bits(T, n):
         for u, v in zip(got[4], ref[4]):
             assert torch.equal(u, v)
         assert got[5] == ref[5]
-        if tol > 0 and maxit >= 300:
-            assert got[1] < maxit, "the stop test must have ended this run"
+        stopped.append(tol > 0 and got[1] < maxit)
+    assert sum(stopped) >= 2, "some runs must have been ended by the in-kernel stop test"
 
 
 def test_two_shards_in_one_process_equal_the_unsharded_solve():
