@@ -504,19 +504,38 @@ def _native_solve(alg, it):
     if isinstance(e.comm, LocalComm) and getattr(e.ctx, "_xchg_comm", None) is not None:
         return None           # pb_solve reads through the attached exchange; an explicit memcpy read-back needs the Python loop
     t0 = time.perf_counter()
-    x = _to_device_copy(it.x0, e.ctx)
-    n = x.numel()
-    grad = f.gradient_buffer() if hasattr(f, "gradient_buffer") else t.empty_like(x)
-    check_vec(grad, n, x.dtype)
-    z, scratch = t.empty_like(x), t.empty_like(x)
-    z_prev = t.empty_like(x) if fast else None
-    x_next = t.empty_like(x) if fast and not it.adaptive else None
-    grad_z = t.empty_like(x) if (not fast and it.adaptive) else None
-    # fixed-stepsize FFB through the device exchange: two spare vectors let pb_solve launch iteration k+1 before the scalars of
-    # iteration k have reached the host (pb_solve_opts.spare_*); `scratch` doubles as the spare gradient buffer
+    # Work vectors.  When x0 lives on the host the solution is copied out at the end, so the device vectors are private to this call and
+    # are kept on the solver object for the next call of the same size (a repeated solve then allocates nothing: the allocator's
+    # occasional cudaMalloc was the largest and least predictable part of the host-buffer call).  A device x0 gets fresh vectors: the
+    # returned solution and `last_state` alias them.
+    host_in = not (isinstance(it.x0, t.Tensor) and it.x0.is_cuda)
     pipelined = fast and not it.adaptive and isinstance(e.comm, DeviceExchangeComm) and getattr(alg, "pipeline", True)
-    spare_x = t.empty_like(x) if pipelined else None
-    spare_z = t.empty_like(x) if pipelined else None
+    n0 = int(np.prod(np.shape(it.x0))) if not isinstance(it.x0, t.Tensor) else it.x0.numel()
+    key = (n0, str(it.x0.dtype).replace("torch.", ""), e.ctx.index, fast, bool(it.adaptive), pipelined)
+    cache = getattr(alg, "_workspace", None) if host_in else None
+    if cache is not None and cache[0] == key:
+        x, z, scratch, z_prev, x_next, grad_z, spare_x, spare_z, own_grad = cache[1]
+        if isinstance(it.x0, t.Tensor):
+            x.copy_(it.x0.detach().contiguous().view(-1), non_blocking=True)
+        else:
+            x.copy_(t.as_tensor(np.ascontiguousarray(it.x0).reshape(-1)))
+    else:
+        x = _to_device_copy(it.x0, e.ctx)
+        z, scratch = t.empty_like(x), t.empty_like(x)
+        z_prev = t.empty_like(x) if fast else None
+        x_next = t.empty_like(x) if fast and not it.adaptive else None
+        grad_z = t.empty_like(x) if (not fast and it.adaptive) else None
+        # fixed-stepsize FFB through the device exchange: two spare vectors let pb_solve run ahead of the stop decision (one launch per
+        # iteration: pb_solve_opts.spare_*; one persistent kernel: the third buffers of its x / z rings); `scratch` doubles as the
+        # spare gradient buffer
+        spare_x = t.empty_like(x) if pipelined else None
+        spare_z = t.empty_like(x) if pipelined else None
+        own_grad = None if hasattr(f, "gradient_buffer") else t.empty_like(x)
+        if host_in:
+            alg._workspace = (key, (x, z, scratch, z_prev, x_next, grad_z, spare_x, spare_z, own_grad))
+    n = x.numel()
+    grad = f.gradient_buffer() if hasattr(f, "gradient_buffer") else own_grad
+    check_vec(grad, n, x.dtype)
     bufs = {b.data_ptr(): b for b in (x, grad, z, scratch, z_prev, x_next, grad_z, spare_x, spare_z) if b is not None}
     n_glob = it.n_global if it.n_global is not None else n * e.comm.size
     opts = L.pb_solve_opts(L.PB_ALG_FFB if fast else L.PB_ALG_FB, 1 if it.adaptive else 0, seq[0], 1 if getattr(alg, "profile", False) else 0, alg.maxit, int(n_glob), float(tol),
