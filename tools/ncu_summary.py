@@ -60,34 +60,46 @@ def launches(csv_path, md_path, round_tag):
         k = r["Kernel Name"]
         agg.setdefault(k, [0, 0.0])
         agg[k][0] += 1
-        agg[k][1] += float(r["Metric Value"])
+        agg[k][1] += float(r["Metric Value"].replace(",", ""))
     tot = sum(v[1] for v in agg.values())
-    out = [f"# Launch list of `bench.py --steps 5 --warmup 3 --no-cpu-baseline` under ncu ({round_tag})", "",
+    out = [f"# Launch list of `bench.py --steps 20 --warmup 3 --no-cpu-baseline` under ncu ({round_tag})", "",
            "`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch times are cold-cache and serialised: compare SHARES.",
-           "The run contains the timed region (k_step), the e2e solve (k_step + k_ew<OP_SUB> = SquaredDistance gradient) and torch's",
-           "random-number fills of the synthetic inputs.", "", "| launches | total us | share | kernel |", "|---|---|---|---|"]
+           "The run contains: the timed region and its warm-up (`k_step_multi<float, L1, LINEAR>`: ONE launch = all K iterations, so 2 launches),",
+           "the kernel-only reference of the roofline block (24 back-to-back `k_step` launches, no exchange), the e2e solve and its warm-up",
+           "(`k_step_multi<float, L1, SQDIST>`: SquaredDistance gradient fused into the step, + one `k_ew<OP_SUB>` for the final f value),",
+           "the counter-based fills of the synthetic inputs (`k_fill_counter`) and the stand-alone exchanges of the final scalar reads (`k_xchg`).",
+           "", "| launches | total us | share | kernel |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| {v[0]} | {v[1] / 1e3:.1f} | {100 * v[1] / tot:.1f}% | `{k[:110]}` |")
     open(md_path, "w").write("\n".join(out) + "\n")
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     g = os.path.join(ROOT, "gpurun_out")
     p = os.path.join(ROOT, "profiles")
     os.makedirs(p, exist_ok=True)
     traffic = {}
-    if os.path.exists(os.path.join(g, "prof_step.ncu-rep")):
-        recs = summarise(os.path.join(g, "prof_step.ncu-rep"), os.path.join(p, f"{tag}_ncu_k_step.md"), "ncu: fused FISTA step K2 at n = 1e8 fp32 (bench.py)", tag)
+    rep = os.path.join(g, f"{tag}_prof_step_multi.ncu-rep")
+    if os.path.exists(rep):
+        # the headline kernel since round 2: ONE persistent launch covers the K iterations of `bench.py --steps K`
+        K = int(os.environ.get("NCU_STEPS", "20"))
+        recs = summarise(rep, os.path.join(p, f"{tag}_ncu_k_step_multi.md"),
+                         f"ncu: persistent multi-iteration FISTA step kernel k_step_multi at n = 1e8 fp32 (`bench.py --steps {K} --warmup 3`: one launch = {K} iterations)", tag)
         r = recs[-1]
-        rd = to_bytes(*r["dram__bytes_read.sum"])
-        wr = to_bytes(*r["dram__bytes_write.sum"])
+        rd = to_bytes(*r["dram__bytes_read.sum"]) / K
+        wr = to_bytes(*r["dram__bytes_write.sum"]) / K
         traffic["k_step_ffb_l1_f32"] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch_at_n": rd + wr, "n": 100000000,
-                                         "algorithmic_bytes": 2e9, "source": f"profiles/{tag}_ncu_k_step.md"}
-    if os.path.exists(os.path.join(g, "prof_lsq.ncu-rep")):
-        summarise(os.path.join(g, "prof_lsq.ncu-rep"), os.path.join(p, f"{tag}_ncu_lsq.md"), "ncu: least-squares kernels (tools/tune_lsq.py, block-diagonal 100 x (100 x 1e5) fp32 first)", tag)
-    if os.path.exists(os.path.join(g, "launches.csv")):
-        launches(os.path.join(g, "launches.csv"), os.path.join(p, f"{tag}_launches.md"), tag)
+                                         "algorithmic_bytes": 2e9, "iterations_in_captured_launch": K, "kernel": r["kernel"],
+                                         "note": "per ITERATION: the captured launch runs K iterations, its dram__bytes are divided by K",
+                                         "source": f"profiles/{tag}_ncu_k_step_multi.md"}
+    for name, title in ((f"{tag}_prof_persist_small", "ncu: persistent on-device solver k_persist_solve, lasso_small ForwardBackward (tools/one_persist.py small fb), one CTA"),
+                        (f"{tag}_prof_lsq", "ncu: least-squares kernels (tools/tune_lsq.py)")):
+        rep = os.path.join(g, name + ".ncu-rep")
+        if os.path.exists(rep):
+            summarise(rep, os.path.join(p, name.replace("_prof_", "_ncu_") + ".md"), title, tag)
+    if os.path.exists(os.path.join(g, f"{tag}_launches.csv")):
+        launches(os.path.join(g, f"{tag}_launches.csv"), os.path.join(p, f"{tag}_launches.md"), tag)
     if traffic:
         json.dump(traffic, open(os.path.join(p, "traffic.json"), "w"), indent=1)
     print("wrote", sorted(os.listdir(p)))
