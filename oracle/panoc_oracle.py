@@ -268,6 +268,7 @@ class PANOCIteration:
         nr = norm2(st.res)
         threshold = np.float64(FBE_x) - sigma * np.float64(R(nr * nr)) + np.float64(tol)
         FBE_new = self._fb(st)                                                 # :199-202
+        st.line_search_trace = (float(FBE_x), float(threshold), float(FBE_new))   # diagnostics: the first test of :205
         for k in range(1, self.max_backtracks + 1):                            # :204-250
             if np.float64(FBE_new) <= threshold:
                 break

@@ -264,6 +264,7 @@ class PANOCIteration:
         sc = self._read(st, fxd, g_of)
         st.f_Ax_d = st.f_Ax                                                                 # :187, :194
         FBE_new = self._fbe_from(st, sc)                                                    # :202
+        st.line_search_trace = (float(FBE_x), float(threshold), float(FBE_new))            # diagnostics: the first test of :205
         moved = False
         for k in range(1, self.max_backtracks + 1):                                         # :204-250
             if np.float64(FBE_new) <= threshold:
