@@ -197,7 +197,7 @@ next_beta!(st::B200FFBState) = st.extrapolation_sequence isa AdaptiveNesterovSeq
 
 # init: fast_forward_backward.jl:73-97 (fixed stepsize: `gamma` or `Lf` given)
 function Base.iterate(iter::FastForwardBackwardIteration{R,<:B200Vector{T}}) where {R,T}
-    iter.gamma === nothing && error("B200Prox: adaptive stepsize is implemented in the Python host only; pass Lf or gamma")
+    iter.gamma === nothing && error("B200Prox: this iterator specialisation covers fixed stepsizes; use b200_solve (pb_solve) for the adaptive line search")
     x = copy(iter.x0)
     grad = similar(x)
     value_and_gradient_into!(grad, iter.f, x)
@@ -312,6 +312,167 @@ function ProximalAlgorithms.default_solution(iter::ProximalAlgorithms.DouglasRac
     y = similar(st.x)                                        # state.y = prox_f(x_in): re-run the pass with y requested
     dr_pass!(iter, st, y.ptr, C_NULL, C_NULL, C_NULL)
     return y
+end
+
+# ======================================================================================================================
+# Whole solves inside the library: pb_solve (csrc/solve.cu, csrc/persist.cu, csrc/step_multi.cu).
+#
+# The iterator specialisations above keep ProximalAlgorithms' own driver loop (one `ccall` + one scalar read-back per iteration).
+# For the built-in terms the library can also run the loop itself -- same kernels, same scalar arithmetic in R, identical
+# iterates and iteration counts (tests/test_gpu_solvers.py::test_native_driver_equals_python_host) -- and then picks the fastest
+# form on its own:
+#   * dense least squares that stays cache resident (the benchmark suite's 5x10 .. 500x1000 problems): ONE persistent cooperative
+#     kernel for the whole solve, line search and Nesterov sequence on the device (`persistent_ctas > 0` in the result);
+#   * fixed stepsize + element-wise gradient source (SquaredDistance): ONE persistent kernel looping over the iterations
+#     (`multi_iter_kernel = 1`), with the per-iteration scalar exchange between GPUs done inside the kernel;
+#   * otherwise one fused kernel per iteration, pipelined one iteration ahead of the stop test.
+# A maintainer wires it in by adding a method for the solver call, e.g.
+#
+#     function (alg::ProximalAlgorithms.IterativeAlgorithm{<:FastForwardBackwardIteration})(; x0::B200Vector, f::B200LeastSquares, g, kwargs...)
+#         alg.stop === default_stop && !alg.verbose || return invoke(...)        # custom stop / display: keep Julia's loop
+#         return b200_solve(f, g, x0; fast = true, maxit = alg.maxit, tol = <tol of the default stopping criterion>, kwargs...)
+#     end
+# ======================================================================================================================
+const PB_F_LSQ_DENSE, PB_F_LSQ_BLOCKDIAG, PB_F_SQDIST, PB_F_LINEAR = Cint(0), Cint(1), Cint(2), Cint(3)
+const PB_ALG_FB, PB_ALG_FFB = Cint(0), Cint(1)
+const PB_SEQ_ADAPTIVE = Cint(0)
+const PB_OPT_FUSED_EXCHANGE, PB_OPT_PERSISTENT, PB_OPT_MULTI_ITER = Cint(4), Cint(5), Cint(6)
+
+struct PbSmooth              # mirrors `struct pb_smooth`
+    kind::Cint
+    pad::Cint
+    m::Int64
+    n::Int64
+    lda::Int64
+    nblk::Int64
+    mb::Int64
+    nb::Int64
+    A::Ptr{Cvoid}
+    b::Ptr{Cvoid}
+    r::Ptr{Cvoid}
+end
+
+struct PbSolveOpts           # mirrors `struct pb_solve_opts`
+    algorithm::Cint
+    adaptive::Cint
+    sequence::Cint
+    profile::Cint
+    maxit::Int64
+    n_global::Int64
+    tol::Cdouble
+    gamma::Cdouble
+    mf::Cdouble
+    constant_beta::Cdouble
+    minimum_gamma::Cdouble
+    reduce_gamma::Cdouble
+    increase_gamma::Cdouble
+    spare_x::Ptr{Cvoid}
+    spare_z::Ptr{Cvoid}
+    spare_grad::Ptr{Cvoid}
+end
+
+mutable struct PbSolveResult  # mirrors `struct pb_solve_result`
+    iterations::Int64
+    backtracks::Int64
+    gamma::Cdouble
+    f_x::Cdouble
+    g_z::Cdouble
+    res_inf::Cdouble
+    warned_small_gamma::Cint
+    persistent_ctas::Cint
+    x::Ptr{Cvoid}
+    grad::Ptr{Cvoid}
+    z::Ptr{Cvoid}
+    z_prev::Ptr{Cvoid}
+    loop_ms::Cdouble
+    step_kernel_ms::Cdouble
+    step_kernel_launches::Int64
+    res_sq::Cdouble
+    gdr::Cdouble
+    gsum::Cdouble
+    multi_iter_kernel::Cint
+    pad::Cint
+    PbSolveResult() = new()
+end
+
+smooth_descriptor(f::B200LeastSquares) = PbSmooth(PB_F_LSQ_DENSE, 0, f.m, f.n, f.m, 0, 0, 0, f.A.ptr, f.b.ptr, f.r.ptr)
+
+"SquaredDistance (benchmark/benchmarks.jl:19-28) on a device vector: f(x) = norm(x - b)^2 / 2."
+struct B200SquaredDistance{T}
+    b::B200Vector{T}
+end
+smooth_descriptor(f::B200SquaredDistance) = PbSmooth(PB_F_SQDIST, 0, 0, length(f.b), 0, 0, 0, 0, C_NULL, f.b.ptr, C_NULL)
+
+"""
+    b200_solve(f, g, x0; fast = true, maxit = 10_000, tol = 1e-8, Lf = nothing, gamma = nothing, mf = 0, n_global = 0, ...)
+
+ForwardBackward (`fast = false`) / FastForwardBackward (`fast = true`) with the reference's keyword arguments and defaults
+(forward_backward.jl:38-48, fast_forward_backward.jl:44-56), run by `pb_solve`.  Returns `(z, iterations, result)`; `x0` is not
+mutated (upload copies, as every reference test asserts).
+"""
+function b200_solve(f, g, x0::B200Vector{T}; fast::Bool = true, maxit::Integer = 10_000, tol::Real = 1e-8, Lf = nothing, gamma = nothing,
+                    adaptive = nothing, mf::Real = 0, minimum_gamma::Real = 1e-7, reduce_gamma::Real = 0.5, increase_gamma::Real = 1.0,
+                    n_global::Integer = 0) where {T}
+    R = real(T)
+    gam = gamma === nothing ? (Lf === nothing ? nothing : 1 / Lf) : gamma          # fast_forward_backward.jl:49
+    adapt = adaptive === nothing ? gam === nothing : adaptive                       # :50
+    x = copy(x0)
+    vecs = [similar(x) for _ in 1:8]                                                # grad, z, z_prev, x_next, grad_z, scratch, spare_x, spare_z
+    grad, z, z_prev, x_next, grad_z, scratch, spare_x, spare_z = vecs
+    fd, gd = Ref(smooth_descriptor(f)), Ref(descriptor(g, T))
+    pipelined = fast && !adapt
+    opts = Ref(PbSolveOpts(fast ? PB_ALG_FFB : PB_ALG_FB, adapt ? 1 : 0, PB_SEQ_ADAPTIVE, 0, maxit, n_global, Float64(tol),
+                           gam === nothing ? 0.0 : Float64(R(gam)), Float64(R(mf)), 0.0, Float64(R(minimum_gamma)), Float64(R(reduce_gamma)),
+                           Float64(R(increase_gamma)), pipelined ? spare_x.ptr : C_NULL, pipelined ? spare_z.ptr : C_NULL,
+                           pipelined ? scratch.ptr : C_NULL))
+    res = PbSolveResult()
+    GC.@preserve x vecs f g begin
+        check(ccall((:pb_solve, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Int64, Ref{PbSmooth}, Ref{PbProx}, Ref{PbSolveOpts}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                     Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{PbSolveResult}),
+                    x.ctx.h, pbdtype(T), length(x), fd, gd, opts, x.ptr, grad.ptr, z.ptr, z_prev.ptr, x_next.ptr, grad_z.ptr, scratch.ptr, res))
+    end
+    res.warned_small_gamma != 0 && @warn "stepsize `gamma` became too small ($(R(res.gamma)))"      # fb_tools.jl:59-61
+    zsol = first(v for v in (x, vecs...) if v.ptr == res.z)                         # buffers are swapped by pointer inside the loop
+    return zsol, Int(res.iterations), res
+end
+
+# ---- one Julia process, all GPUs of the node (SURVEY.md section 8b "Threading"): one context and one task per device ------------
+"""
+    B200World(devices) -> contexts connected for the in-kernel scalar exchange (pb_xchg_connect_local)
+
+Row-shard every n-vector over the contexts (32-element aligned ranges), then run the SAME `b200_solve` on every shard from its own
+task with `n_global = n`: the step kernels exchange their scalar blocks over NVLink inside the kernel, every rank takes identical
+decisions, and the concatenated shards equal the single-GPU solution bit for bit (tests/test_gpu_local_world.py).
+Rule (as for NCCL): no device-wide synchronisation (allocation, `cudaDeviceSynchronize`) on one rank while another is inside a solve.
+"""
+struct B200World
+    ctxs::Vector{B200Context}
+end
+function B200World(devices::AbstractVector{<:Integer})
+    ctxs = [B200Context(d) for d in devices]
+    P = length(ctxs)
+    for (r, c) in enumerate(ctxs)
+        check(ccall((:pb_xchg_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}), c.h, r - 1, P, C_NULL))
+    end
+    hs = [c.h for c in ctxs]
+    check(ccall((:pb_xchg_connect_local, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), hs, P))
+    for c in ctxs
+        check(ccall((:pb_ctx_set_option, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), c.h, PB_OPT_FUSED_EXCHANGE, 1))
+    end
+    return B200World(ctxs)
+end
+
+"Run `solve_shard(rank, ctx)` (which calls `b200_solve` on that rank's shard) on every context concurrently; one task per GPU."
+function on_every_gpu(solve_shard, w::B200World)
+    out = Vector{Any}(undef, length(w.ctxs))
+    Threads.@sync for (r, c) in enumerate(w.ctxs)
+        Threads.@spawn begin
+            check(ccall((:pb_ctx_make_current, LIB), Cint, (Ptr{Cvoid},), c.h))
+            out[r] = solve_shard(r - 1, c)
+        end
+    end
+    return out
 end
 
 end # module
