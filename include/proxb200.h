@@ -120,6 +120,7 @@ enum {
   PB_OPT_MULTI_ITER = 6,    /* pb_solve, fixed-stepsize FFB with an element-wise gradient source (LinearFunction, SquaredDistance):
                                0 = auto (ONE persistent kernel loops over the iterations, csrc/step_multi.cu; off when contexts
                                of one process share a GPU), -1 = never (one launch per iteration), 1 = always.  Same results */
+  PB_OPT_GEMV_SCALAR = 7,   /* 1: r = A x - b with the thread-per-row kernel (4-byte loads) instead of 16-byte row packs; same bits     */
   PB_OPT_PERSISTENT = 5     /* pb_solve on cache-resident dense least squares (m*n*sizeof <= 8 MB): 0 = auto (whole solve
                                in one persistent cooperative kernel, csrc/persist.cu), -1 = never (one kernel per
                                operation), 1..32 = persistent on at most that many CTAs.  Results do not depend on it */

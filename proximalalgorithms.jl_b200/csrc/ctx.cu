@@ -5,6 +5,8 @@
 
 #include "common.cuh"
 
+size_t pb_multi_ws_bytes();   // step_multi.cu
+
 static thread_local char g_err[512] = "";
 
 void pb_set_error(const char* fmt, ...) {
@@ -66,6 +68,7 @@ extern "C" int pb_ctx_create(int device, void* stream, int borrow_stream, pb_ctx
   bool ok = cudaMalloc(&c->scalars_own, PB_NSCALARS * sizeof(double)) == cudaSuccess &&
             cudaMallocHost(&c->scalars_host, PB_NSCALARS * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&c->ws, sizeof(PbWorkspace)) == cudaSuccess &&
+            cudaMalloc(&c->multi_ws, pb_multi_ws_bytes()) == cudaSuccess &&
             cudaMemsetAsync(c->scalars_own, 0, PB_NSCALARS * sizeof(double), c->stream) == cudaSuccess &&
             cudaMemsetAsync(c->ws, 0, sizeof(PbWorkspace), c->stream) == cudaSuccess &&
             cudaStreamSynchronize(c->stream) == cudaSuccess;
@@ -149,6 +152,10 @@ extern "C" int pb_ctx_set_option(pb_ctx* c, int option, int value) {
     case PB_OPT_PERSISTENT:
       PB_REQUIRE(value >= -1 && value <= 32, "persistent mode must be -1, 0 or 1..32");
       c->persist_mode = value;
+      return PB_OK;
+    case PB_OPT_GEMV_SCALAR:
+      PB_REQUIRE(value == 0 || value == 1, "gemv scalar mode must be 0 or 1");
+      c->gemv_scalar = value;
       return PB_OK;
     case PB_OPT_MULTI_ITER:
       PB_REQUIRE(value >= -1 && value <= 1, "multi-iteration mode must be -1, 0 or 1");

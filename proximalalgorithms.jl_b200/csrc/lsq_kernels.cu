@@ -54,6 +54,63 @@ __global__ void __launch_bounds__(GEMV_ROWS* GEMV_CL)
   }
 }
 
+// Same product, same summation order per row (4 column lanes, each a sequential FMA chain over its columns, lanes added
+// ((l0 + l1) + l2) + l3), but every thread owns ONE 16-byte pack of VEC consecutive rows: a warp instruction moves 512 bytes of a
+// column instead of 128, and UNROLL packs per thread are in flight.  The thread-per-row kernel above reached 0.59 of the measured HBM
+// peak on a tall dense matrix (10000 x 100000 fp32, profiles/r01_ncu_lsq.md: 62 % DRAM, 4-byte loads); results are bit-identical.
+// RP = row packs per CTA (block = RP x 4 threads): 128 for tall columns, 32 when a column has at most 32 packs.
+template <typename T, int RP>
+__global__ void __launch_bounds__(RP* GEMV_CL)
+    k_gemv_n_partial_v(const T* __restrict__ A, int64_t lda, int64_t blk_stride, const T* __restrict__ x, T* __restrict__ partial,
+                       int64_t mb, int64_t nb, int64_t nblk, int64_t chunk_cols) {
+  constexpr int VEC = 16 / sizeof(T);
+  __shared__ Pack<T, VEC> sh[GEMV_CL][RP];
+  const int rl = threadIdx.x % RP, cl = threadIdx.x / RP;
+  const int64_t k = blockIdx.z;
+  const int64_t pk = (int64_t)blockIdx.x * RP + rl;          // row pack of this thread
+  const int64_t npk = mb / VEC;
+  const int64_t c0 = (int64_t)blockIdx.y * chunk_cols;
+  int64_t c1 = c0 + chunk_cols;
+  if (c1 > nb) c1 = nb;
+  const T* __restrict__ Ak = A + k * blk_stride + pk * VEC;
+  const T* __restrict__ xk = x + k * nb;
+  Pack<T, VEC> acc;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc.v[e] = T(0);
+  if (pk < npk) {
+    int64_t j = c0 + cl;
+    for (; j + (GEMV_UNROLL - 1) * GEMV_CL < c1; j += GEMV_UNROLL * GEMV_CL) {
+      Pack<T, VEC> a[GEMV_UNROLL];
+      T xv[GEMV_UNROLL];
+#pragma unroll
+      for (int u = 0; u < GEMV_UNROLL; ++u) {
+        a[u] = ld_pack<T, VEC, false>(Ak + (j + u * GEMV_CL) * lda);
+        xv[u] = __ldg(xk + j + u * GEMV_CL);
+      }
+#pragma unroll
+      for (int u = 0; u < GEMV_UNROLL; ++u)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc.v[e] = fma(a[u].v[e], xv[u], acc.v[e]);
+    }
+    for (; j < c1; j += GEMV_CL) {
+      const Pack<T, VEC> a = ld_pack<T, VEC, false>(Ak + j * lda);
+      const T xv = __ldg(xk + j);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc.v[e] = fma(a.v[e], xv, acc.v[e]);
+    }
+  }
+  sh[cl][rl] = acc;
+  __syncthreads();
+  if (cl == 0 && pk < npk) {
+    Pack<T, VEC> s = sh[0][rl];
+#pragma unroll
+    for (int c = 1; c < GEMV_CL; ++c)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) s.v[e] += sh[c][rl].v[e];
+    *reinterpret_cast<Pack<T, VEC>*>(partial + ((int64_t)blockIdx.y * nblk + k) * mb + pk * VEC) = s;
+  }
+}
+
 // partial product for SHORT columns (mb < 64, e.g. the 4 x 128000 blocks of the group-lasso workload): the thread-per-row
 // kernel above would keep mb of its 128 row lanes busy.  Mirror image of k_gemv_t_sub: LPC lanes share one column, each lane
 // owns up to KP 16-byte packs of it and accumulates a_ij * x_j into its own row accumulators while the CTA sweeps the
@@ -293,6 +350,18 @@ static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
       }
     }
 #undef PB_LAUNCH_NSUB
+  } else if (ctx->gemv_scalar == 0 && mb % (16 / (int64_t)sizeof(T)) == 0 && lda % (16 / (int64_t)sizeof(T)) == 0 &&
+             blk_stride % (16 / (int64_t)sizeof(T)) == 0 && M % (16 / (int64_t)sizeof(T)) == 0 && pb_aligned16(A) && pb_aligned16(partial)) {
+    // 16-byte row packs (same order, bit-identical to the thread-per-row kernel below)
+    constexpr int VEC = 16 / sizeof(T);
+    const int64_t npk = mb / VEC;
+    if (npk <= 32) {
+      dim3 grid(1, (unsigned)nchunk, (unsigned)nblk);
+      k_gemv_n_partial_v<T, 32><<<grid, 32 * GEMV_CL, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk, chunk_cols);
+    } else {
+      dim3 grid((unsigned)((npk + 127) / 128), (unsigned)nchunk, (unsigned)nblk);
+      k_gemv_n_partial_v<T, 128><<<grid, 128 * GEMV_CL, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk, chunk_cols);
+    }
   } else {
     dim3 grid((unsigned)row_tiles, (unsigned)nchunk, (unsigned)nblk);
     k_gemv_n_partial<T><<<grid, GEMV_ROWS * GEMV_CL, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk,

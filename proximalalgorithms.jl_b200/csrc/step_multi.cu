@@ -305,6 +305,10 @@ __global__ void __launch_bounds__(SM_BLOCK, 2) k_step_multi(MultiParams p) {
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
+// The workspace is allocated when the context is created, never inside a solve: cudaMalloc may wait for the device to go idle, and on
+// a device shared by several contexts a peer's persistent kernel may already be spinning there, waiting for THIS rank's kernel.
+size_t pb_multi_ws_bytes() { return sizeof(MultiWs); }
+
 bool pb_multi_eligible(const pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o, const void* x_next) {
   (void)dtype;
   if (ctx->multi_mode < 0) return false;
@@ -343,9 +347,7 @@ static int multi_launch_prox(pb_ctx* ctx, const MultiParams& p, int grid, bool h
 int pb_multi_run(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o, void* const X[3],
                  void* const Z[3], int64_t* k_out, double comb[4], float* kernel_ms) {
   PB_CHECK_CUDA(cudaSetDevice(ctx->device));
-  if (!ctx->multi_ws) {
-    PB_CHECK_CUDA(cudaMalloc(&ctx->multi_ws, sizeof(MultiWs)));
-  }
+  PB_REQUIRE(ctx->multi_ws != nullptr, "context has no multi-iteration workspace");
   PB_CHECK_CUDA(cudaMemsetAsync(ctx->multi_ws, 0, sizeof(MultiWs), ctx->stream));
   MultiParams p;
   memset(&p, 0, sizeof(p));

@@ -106,3 +106,26 @@ def test_lsq_argument_errors():
     assert c.lib.pb_lsq_dense_gradient(c.h, 0, 4, 2, None, 4, ptr(x), ptr(x)) == 1                 # null A
     assert c.lib.pb_lsq_blockdiag_residual(c.h, 0, -1, 2, 2, ptr(x), ptr(x), ptr(x), ptr(x)) == 1
     assert c.lib.pb_last_error()
+
+
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("nblk,mb,nb", [(1, 100, 1000), (1, 64, 333), (3, 128, 2000), (1, 500, 1000), (1, 1024, 70), (2, 200, 5003), (1, 10000, 300), (5, 72, 129)])
+def test_row_pack_residual_kernel_is_bit_identical_to_thread_per_row(T, nblk, mb, nb):
+    """k_gemv_n_partial_v (16-byte row packs) keeps the summation order of k_gemv_n_partial per row: identical r and ||r||^2."""
+    rng = np.random.default_rng(mb * 7 + nb)
+    A = torch.as_tensor(rng.standard_normal((nblk, nb, mb)).astype(T)).cuda()
+    b = torch.as_tensor(rng.standard_normal(nblk * mb).astype(T)).cuda()
+    x = torch.as_tensor(rng.standard_normal(nblk * nb).astype(T)).cuda()
+    c = G.ctx()
+    out = []
+    for mode in (1, 0):
+        L.check(c.lib.pb_ctx_set_option(c.h, L.PB_OPT_GEMV_SCALAR, mode))
+        r = torch.empty_like(b)
+        L.check(c.lib.pb_lsq_blockdiag_residual(c.h, G.dt(T), nblk, mb, nb, ptr(A), ptr(x), ptr(b), ptr(r)))
+        row = c.read_scalars()
+        out.append((r.clone(), row[L.PB_S_AUX], row[L.PB_S_AUX + 1]))
+    L.check(c.lib.pb_ctx_set_option(c.h, L.PB_OPT_GEMV_SCALAR, 0))
+    assert torch.equal(out[0][0], out[1][0])
+    assert out[0][1:] == out[1][1:]
+    r64 = np.einsum("kji,kj->ki", A.cpu().numpy().astype(np.float64), x.cpu().numpy().astype(np.float64).reshape(nblk, nb)).reshape(-1) - b.cpu().numpy()
+    assert np.allclose(out[1][0].cpu().numpy(), r64, rtol=0, atol=_tol(T, nb) * 50 * np.max(np.abs(r64)))
