@@ -120,6 +120,9 @@ enum {
   PB_OPT_MULTI_ITER = 6,    /* pb_solve, fixed-stepsize FFB with an element-wise gradient source (LinearFunction, SquaredDistance):
                                0 = auto (ONE persistent kernel loops over the iterations, csrc/step_multi.cu; off when contexts
                                of one process share a GPU), -1 = never (one launch per iteration), 1 = always.  Same results */
+  PB_OPT_LSQ_FUSED = 8,     /* pb_lsq_blockdiag_value_and_gradient: 0 = auto (ONE persistent kernel that reads every block of A from HBM
+                               once and its second sweep from L2 when A exceeds L2 and a block fits it, csrc/lsq_fused.cu), -1 = never
+                               (residual kernel + gradient kernel), k = 1..8: always, keeping k blocks between the sweeps. Same bits */
   PB_OPT_GEMV_SCALAR = 7,   /* 1: r = A x - b with the thread-per-row kernel (4-byte loads) instead of 16-byte row packs; same bits     */
   PB_OPT_PERSISTENT = 5     /* pb_solve on cache-resident dense least squares (m*n*sizeof <= 8 MB): 0 = auto (whole solve
                                in one persistent cooperative kernel, csrc/persist.cu), -1 = never (one kernel per
@@ -206,6 +209,12 @@ int pb_lsq_blockdiag_residual(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, 
                               const void* x, const void* b, void* r);
 int pb_lsq_blockdiag_gradient(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, int64_t nb, const void* A,
                               const void* r, void* grad);
+/* value AND gradient of the block-diagonal term in one call: r = A x - b, AUX = ||r||^2, grad = A' r, bit-identical to
+ * pb_lsq_blockdiag_residual + pb_lsq_blockdiag_gradient.  For matrices beyond L2 whose blocks fit it, one persistent kernel streams every
+ * block from HBM once (chunk partials), assembles r_k, and re-reads the block for A_k' r_k while it is still L2 resident
+ * (csrc/lsq_fused.cu): ~1 sweep of HBM traffic per value_and_gradient instead of 2 (BM:11-17 per block). */
+int pb_lsq_blockdiag_value_and_gradient(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, int64_t nb, const void* A, const void* x,
+                                        const void* b, void* r, void* grad);
 /* SquaredDistance (BM:19-28): grad = x - b, AUX = ||x - b||^2. */
 int pb_sqdist(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* b, void* grad);
 

@@ -226,6 +226,18 @@ __global__ void __launch_bounds__(PB_BLOCK) k_gemv_t(const T* __restrict__ A, in
     const T* __restrict__ rk = r + k * mb;
     T acc = T(0);
     int64_t i = lane;
+    // tall columns: 16 loads per lane in flight (2 KB per warp) -- with 4 the kernel was latency bound at ~0.45 of the HBM peak on a
+    // 10000-row column; the FMA order (rows lane, lane + 32, ... ascending) is unchanged
+    for (; i + 15 * 32 < mb; i += 16 * 32) {
+      T a_[16], r_[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        a_[u] = __ldg(a + i + u * 32);
+        r_[u] = __ldg(rk + i + u * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) acc = fma(a_[u], r_[u], acc);
+    }
     for (; i + 3 * 32 < mb; i += 4 * 32) {
       const T a0 = __ldg(a + i), a1 = __ldg(a + i + 32), a2 = __ldg(a + i + 64), a3 = __ldg(a + i + 96);
       const T r0 = __ldg(rk + i), r1 = __ldg(rk + i + 32), r2 = __ldg(rk + i + 64), r3 = __ldg(rk + i + 96);

@@ -146,8 +146,7 @@ struct Solver {
         if ((rc = residual(v))) return rc;
         return pb_lsq_dense_gradient(ctx, dtype, f->m, f->n, f->A, f->lda, f->r, grad_out);
       case PB_F_LSQ_BLOCKDIAG:
-        if ((rc = residual(v))) return rc;
-        return pb_lsq_blockdiag_gradient(ctx, dtype, f->nblk, f->mb, f->nb, f->A, f->r, grad_out);
+        return pb_lsq_blockdiag_value_and_gradient(ctx, dtype, f->nblk, f->mb, f->nb, f->A, v, f->b, f->r, grad_out);
       case PB_F_SQDIST:
         return pb_sqdist(ctx, dtype, n, v, f->b, grad_out);
       case PB_F_LINEAR:

@@ -274,9 +274,11 @@ class BlockDiagLeastSquares:
 
     def value_and_gradient_into(self, ctx, x, grad):
         self.calls += 1
-        val = self._residual(ctx, x)
-        L.check(ctx.lib.pb_lsq_blockdiag_gradient(ctx.h, pb_dtype(self.R), self.nblk, self.mb, self.nb, ptr(self.A), ptr(self.r), ptr(grad)))
-        return val
+        check_vec(x, self.n, self.A.dtype)
+        # one call: for matrices beyond L2 the library reads every block from HBM once and sweeps it again from L2 (csrc/lsq_fused.cu)
+        L.check(ctx.lib.pb_lsq_blockdiag_value_and_gradient(ctx.h, pb_dtype(self.R), self.nblk, self.mb, self.nb, ptr(self.A), ptr(x), ptr(self.b),
+                                                            ptr(self.r), ptr(grad)))
+        return Deferred(lambda row, comb: _sq_half(self.R, comb.aux if comb is not None else row[L.PB_S_AUX] + row[L.PB_S_AUX + 1]))
 
     def value_into(self, ctx, x):
         self.calls += 1

@@ -129,3 +129,30 @@ def test_row_pack_residual_kernel_is_bit_identical_to_thread_per_row(T, nblk, mb
     assert out[0][1:] == out[1][1:]
     r64 = np.einsum("kji,kj->ki", A.cpu().numpy().astype(np.float64), x.cpu().numpy().astype(np.float64).reshape(nblk, nb)).reshape(-1) - b.cpu().numpy()
     assert np.allclose(out[1][0].cpu().numpy(), r64, rtol=0, atol=_tol(T, nb) * 50 * np.max(np.abs(r64)))
+
+
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("nblk,mb,nb", [(5, 100, 5003), (7, 64, 2100), (4, 128, 40_000), (9, 200, 3000), (1, 100, 700), (12, 72, 64), (3, 100, 100_000)])
+@pytest.mark.parametrize("live", [1, 2, 3])
+def test_fused_blockdiag_value_and_gradient_is_bit_identical(T, nblk, mb, nb, live):
+    """csrc/lsq_fused.cu (every block read from HBM once, second sweep from L2, dynamic N / T work units through a TMA ring) against the
+    residual kernel followed by the gradient kernel: same r, grad and ||r||^2, bit for bit, whatever the throttle depth."""
+    if T == np.float64 and mb == 200:
+        pytest.skip("row packs of a column must fit one CTA (mb <= 128 in Float64): this shape takes the two-kernel path")
+    rng = np.random.default_rng(mb + nb + nblk)
+    A = torch.as_tensor(rng.standard_normal((nblk, nb, mb)).astype(T)).cuda()
+    b = torch.as_tensor(rng.standard_normal(nblk * mb).astype(T)).cuda()
+    x = torch.as_tensor(rng.standard_normal(nblk * nb).astype(T)).cuda()
+    c = G.ctx()
+    out = []
+    for mode in (-1, live):
+        L.check(c.lib.pb_ctx_set_option(c.h, L.PB_OPT_LSQ_FUSED, mode))
+        r, grad = torch.full_like(b, float("nan")), torch.full_like(x, float("nan"))
+        l0 = c.launches()
+        L.check(c.lib.pb_lsq_blockdiag_value_and_gradient(c.h, G.dt(T), nblk, mb, nb, ptr(A), ptr(x), ptr(b), ptr(r), ptr(grad)))
+        row = c.read_scalars()
+        out.append((r.clone(), grad.clone(), row[L.PB_S_AUX], row[L.PB_S_AUX + 1], c.launches() - l0))
+    L.check(c.lib.pb_ctx_set_option(c.h, L.PB_OPT_LSQ_FUSED, 0))
+    assert out[1][4] == 1 and out[0][4] >= 2, "the fused form is one launch"
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[0][2] + out[0][3] == out[1][2] + out[1][3]
