@@ -65,23 +65,22 @@ __device__ __forceinline__ void bf_st_rel(unsigned int* p, unsigned int v) {
 
 enum { BF_UNIT_N = 0, BF_UNIT_T = 1, BF_UNIT_EXIT = 2 };
 
-// thread 0: take the next work unit (T units of ready blocks first, then the next N unit if its throttle allows)
-__device__ int bf_acquire(const BfParams& p, int* k_out, int* c_out) {
+// thread 0: take the next work unit (T units of ready blocks first, then the next N unit if its throttle allows).  `tf` is this CTA's
+// cached lower bound of the first block with unclaimed T units; a claim costs one atomic round trip in the common case.
+__device__ int bf_acquire(const BfParams& p, unsigned int& tf, int* k_out, int* c_out) {
   const unsigned int NU = (unsigned int)p.nchunk;
-  const unsigned int total = (unsigned int)p.nblk * NU;
+  const unsigned int nblk = (unsigned int)p.nblk;
+  const unsigned int total = nblk * NU;
   for (;;) {
-    const unsigned int tf = bf_ld_acq(&p.st->t_front);
-    unsigned int hi = tf + (unsigned int)p.live + 1u;
-    if (hi > (unsigned int)p.nblk) hi = (unsigned int)p.nblk;
-    for (unsigned int kt = tf; kt < hi; ++kt) {
-      if (bf_ld_acq(&p.blk[kt].ready) && bf_ld_acq(&p.blk[kt].t_next) < NU) {
-        const unsigned int c = atomicAdd(&p.blk[kt].t_next, 1u);
-        if (c < NU) {
-          *k_out = (int)kt;
-          *c_out = (int)c;
-          return BF_UNIT_T;
-        }
+    // T units: the oldest block that still has some
+    while (tf < nblk && bf_ld_acq(&p.blk[tf].ready)) {
+      const unsigned int c = atomicAdd(&p.blk[tf].t_next, 1u);
+      if (c < NU) {
+        *k_out = (int)tf;
+        *c_out = (int)c;
+        return BF_UNIT_T;
       }
+      tf += 1;                                   // every T unit of this block is taken
     }
     const unsigned int idx = bf_ld_acq(&p.st->n_next);
     if (idx < total) {
@@ -94,10 +93,10 @@ __device__ int bf_acquire(const BfParams& p, int* k_out, int* c_out) {
         }
         continue;
       }
-    } else if (tf >= (unsigned int)p.nblk) {
+    } else if (tf >= nblk) {
       return BF_UNIT_EXIT;
     }
-    __nanosleep(200);
+    __nanosleep(100);
   }
 }
 
@@ -130,11 +129,12 @@ __global__ void __launch_bounds__(BF_BLOCK, 2) k_bd_fused(BfParams p) {
   }
   __syncthreads();
   unsigned long long it_global = 0;              // tiles consumed so far by this CTA: stage = it % stages, parity = (it / stages) & 1
+  unsigned int tf_cache = 0;                     // thread 0: first block that may still have unclaimed T units
 
   for (;;) {
     if (tid == 0) {
       int k_, c_;
-      ctl[0] = bf_acquire(p, &k_, &c_);
+      ctl[0] = bf_acquire(p, tf_cache, &k_, &c_);
       ctl[1] = k_;
       ctl[2] = c_;
     }
@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(BF_BLOCK, 2) k_bd_fused(BfParams p) {
       const int pre = ntile < p.stages ? ntile : p.stages;
       for (int t = 0; t < pre; ++t) issue(t);
     }
-    (void)tile_bytes;
 
     if (type == BF_UNIT_N) {
       // ---- partial[c][k][:] = A_k[:, chunk] x_k[chunk]: thread (pk, cl) owns row pack pk and the columns c0 + cl, c0 + cl + 4, ...
@@ -208,13 +207,31 @@ __global__ void __launch_bounds__(BF_BLOCK, 2) k_bd_fused(BfParams p) {
       __syncthreads();
       if (ctl[3]) {
         // ---- last N unit of block k: r_k = (chunk partials in chunk order) - b_k, this block's share of ||r||^2, then `ready`
+        // (on the critical path of the whole pipeline: the nchunk x mb partials are first pulled from L2 by ALL threads with independent
+        //  loads into the idle ring, then each row is summed in chunk order from shared memory -- not nchunk dependent L2 round trips)
         __threadfence();
+        T* stage = ring;                          // every tile of this unit has been consumed and nothing is in flight
+        const int npart = p.nchunk * (int)mb;
+        const bool staged = (size_t)npart * sizeof(T) <= (size_t)p.stages * tile_bytes;
+        if (staged) {
+          for (int q = tid; q < npart; q += BF_BLOCK) {
+            const int cc = q / (int)mb, i = q - cc * (int)mb;
+            stage[q] = __ldcg(partial + (int64_t)cc * M + (int64_t)k * mb + i);
+          }
+          __syncthreads();
+        }
         Acc<1, 1> a1;
         a1.clear();
         for (int64_t i = tid; i < mb; i += BF_BLOCK) {
           const int64_t gi = (int64_t)k * mb + i;
-          T s_ = __ldcg(partial + gi);
-          for (int cc = 1; cc < p.nchunk; ++cc) s_ += __ldcg(partial + (int64_t)cc * M + gi);
+          T s_;
+          if (staged) {
+            s_ = stage[i];
+            for (int cc = 1; cc < p.nchunk; ++cc) s_ += stage[(size_t)cc * mb + i];
+          } else {
+            s_ = __ldcg(partial + gi);
+            for (int cc = 1; cc < p.nchunk; ++cc) s_ += __ldcg(partial + (int64_t)cc * M + gi);
+          }
           const T rv = bvec ? sub_rn(s_, __ldg(bvec + gi)) : s_;
           __stcg(r + gi, rv);
           if (COMP)
