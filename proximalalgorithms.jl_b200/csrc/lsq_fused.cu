@@ -18,6 +18,7 @@
 //
 // Summation orders are those of k_gemv_n_partial(_v) + k_gemv_n_combine and k_gemv_t_sub (lsq_kernels.cu, rule in lsq_order.h):
 // r, grad and ||r||^2 are bit-identical to the two-kernel path (tests/test_gpu_lsq.py).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -33,6 +34,7 @@ struct BfState {                 // global bookkeeping, zeroed before every laun
   unsigned int t_front;          // lowest block whose T units are not all done
   unsigned int exit_ticket;
   unsigned int pad[29];
+  unsigned long long prof[8];    // ns summed over CTAs: 0 acquiring, 1 N units, 2 T units, 3 assembling r_k; 4 / 5: N / T units done
 };
 struct BfBlock {                 // per block
   unsigned int n_done, ready, t_next, t_done;
@@ -132,11 +134,15 @@ __global__ void __launch_bounds__(BF_BLOCK, 2) k_bd_fused(BfParams p) {
   unsigned int tf_cache = 0;                     // thread 0: first block that may still have unclaimed T units
 
   for (;;) {
+    unsigned long long t_a = 0;
     if (tid == 0) {
       int k_, c_;
+      t_a = globaltimer_ns();
       ctl[0] = bf_acquire(p, tf_cache, &k_, &c_);
       ctl[1] = k_;
       ctl[2] = c_;
+      atomicAdd(&p.st->prof[0], globaltimer_ns() - t_a);
+      t_a = globaltimer_ns();
     }
     __syncthreads();
     const int type = ctl[0], k = ctl[1], c = ctl[2];
@@ -203,6 +209,9 @@ __global__ void __launch_bounds__(BF_BLOCK, 2) k_bd_fused(BfParams p) {
       if (tid == 0) {
         __threadfence();
         ctl[3] = (atomicAdd(&p.blk[k].n_done, 1u) + 1u == (unsigned int)p.nchunk) ? 1 : 0;
+        atomicAdd(&p.st->prof[1], globaltimer_ns() - t_a);
+        atomicAdd(&p.st->prof[4], 1ull);
+        t_a = globaltimer_ns();
       }
       __syncthreads();
       if (ctl[3]) {
@@ -248,6 +257,7 @@ __global__ void __launch_bounds__(BF_BLOCK, 2) k_bd_fused(BfParams p) {
         if (tid == 0) {
           __threadfence();
           bf_st_rel(&p.blk[k].ready, 1u);
+          atomicAdd(&p.st->prof[3], globaltimer_ns() - t_a);
         }
       }
     } else {
@@ -295,6 +305,8 @@ __global__ void __launch_bounds__(BF_BLOCK, 2) k_bd_fused(BfParams p) {
         it_global += 1;
       }
       if (tid == 0) {
+        atomicAdd(&p.st->prof[2], globaltimer_ns() - t_a);
+        atomicAdd(&p.st->prof[5], 1ull);
         const unsigned int d = atomicAdd(&p.blk[k].t_done, 1u) + 1u;
         if (d == (unsigned int)p.nchunk) {        // block k is finished: move the front past every finished block
           unsigned int tf = bf_ld_acq(&p.st->t_front);
@@ -344,7 +356,14 @@ static int bd_fused_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
   const double blk_bytes = (double)mb * (double)nb * sizeof(T), tot_bytes = blk_bytes * (double)nblk;
   // the two-kernel path is as good while everything fits L2 anyway; a block must leave room for LIVE = 2 of them in L2
   if (ord.n_sub || !ord.t_sub || mb % VEC != 0 || npk * 4 > BF_BLOCK || nblk > 0x3fffffLL / ord.nchunk) return PB_OK;
-  if (ctx->lsq_fused == 0 && (tot_bytes < 96.0 * 1024 * 1024 || blk_bytes > 44.0 * 1024 * 1024 || nblk < 4)) return PB_OK;
+  // MEASURED (profiles/r02_lsq_fused.md): this form is 3-9x SLOWER than the two kernels on configs[1] -- one CTA streams ~20 GB/s through
+  // its ring whether the bytes come from HBM or L2, the summation-order rule gives 64 independent units per block, and only ~2 blocks
+  // (80 MB) may sit between the sweeps, so ~128 of the 296 CTAs have work at any time.  It is therefore never chosen automatically
+  // (PB_OPT_LSQ_FUSED = k > 0 forces it; the tests do, for the bit-parity of its bookkeeping); the single-sweep answer for fixed-stepsize
+  // FISTA is lsq_fista.cu, which needs no second sweep at all.
+  (void)tot_bytes;
+  (void)blk_bytes;
+  if (ctx->lsq_fused == 0) return PB_OK;
   if (!pb_aligned16(A) || !pb_aligned16(r) || !pb_aligned16(x)) return PB_OK;
   const size_t col_bytes = (size_t)mb * sizeof(T);
   const size_t tile_bytes = BF_TILE_COLS * col_bytes;
@@ -399,6 +418,14 @@ static int bd_fused_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
   PB_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(BF_BLOCK), args, smem, ctx->stream));
   ctx->launches++;
   *done = true;
+  if (getenv("PROXB200_LSQ_FUSED_PROF")) {       // diagnostics: where the CTAs spent their time (ns summed over CTAs)
+    unsigned long long prof[8];
+    PB_CHECK_CUDA(cudaMemcpyAsync(prof, &p.st->prof[0], sizeof(prof), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    fprintf(stderr, "lsq_fused: grid %lld stages %d live %d | per CTA us: acquire %.1f  N %.1f  T %.1f  assemble %.1f | N units %llu (%.1f us each)  T units %llu (%.1f us each)\n",
+            (long long)grid, stages, p.live, prof[0] / 1e3 / grid, prof[1] / 1e3 / grid, prof[2] / 1e3 / grid, prof[3] / 1e3 / grid, prof[4],
+            prof[4] ? prof[1] / 1e3 / prof[4] : 0.0, prof[5], prof[5] ? prof[2] / 1e3 / prof[5] : 0.0);
+  }
   return PB_OK;
 }
 
