@@ -120,6 +120,9 @@ enum {
   PB_OPT_MULTI_ITER = 6,    /* pb_solve, fixed-stepsize FFB with an element-wise gradient source (LinearFunction, SquaredDistance):
                                0 = auto (ONE persistent kernel loops over the iterations, csrc/step_multi.cu; off when contexts
                                of one process share a GPU), -1 = never (one launch per iteration), 1 = always.  Same results */
+  PB_OPT_LSQ_FISTA = 9,     /* pb_solve, fixed-stepsize FFB on a block-diagonal least-squares term: 0 = auto (ONE sweep of A per iteration:
+                               gradient, fused step and the next residual's partial products from the same tiles, csrc/lsq_fista.cu, when A
+                               exceeds 64 MB), -1 = never (residual + gradient + step kernels), 1 = whenever the shape allows.  Same bits   */
   PB_OPT_LSQ_FUSED = 8,     /* pb_lsq_blockdiag_value_and_gradient: 0 = auto (ONE persistent kernel that reads every block of A from HBM
                                once and its second sweep from L2 when A exceeds L2 and a block fits it, csrc/lsq_fused.cu), -1 = never
                                (residual kernel + gradient kernel), k = 1..8: always, keeping k blocks between the sweeps. Same bits */

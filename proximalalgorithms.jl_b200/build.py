@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 INCLUDE = os.path.join(ROOT, "include")
 LIBNAME = "libproxb200.so"
-SOURCES = ["ctx.cu", "step_kernels.cu", "step_tma.cu", "lsq_kernels.cu", "xchg.cu", "solve.cu", "qn_kernels.cu", "dr_kernels.cu", "lsq_prox.cu", "tv_kernels.cu", "stencil_kernels.cu", "panoc_solve.cu", "util_kernels.cu", "persist.cu", "step_multi.cu", "lsq_fused.cu"]
+SOURCES = ["ctx.cu", "step_kernels.cu", "step_tma.cu", "lsq_kernels.cu", "xchg.cu", "solve.cu", "qn_kernels.cu", "dr_kernels.cu", "lsq_prox.cu", "tv_kernels.cu", "stencil_kernels.cu", "panoc_solve.cu", "util_kernels.cu", "persist.cu", "step_multi.cu", "lsq_fused.cu", "lsq_fista.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -41,6 +41,7 @@ struct pb_ctx {
   int step_impl;       // 0 = default, 1 = register pipeline, 2 = TMA bulk ring
   int persist_mode;    // PB_OPT_PERSISTENT: 0 auto, -1 never, k > 0 at most k CTAs
   long long persist_cycles[8];   // per-phase clock64() totals of the last profiled persistent solve
+  int lsq_fista;       // PB_OPT_LSQ_FISTA: 0 auto, -1 never, 1 always (when the shape allows)
   int lsq_fused;       // PB_OPT_LSQ_FUSED: 0 auto, -1 never, k > 0 always with k blocks kept between the two sweeps
   int gemv_scalar;     // PB_OPT_GEMV_SCALAR: 1 = thread-per-row residual kernel (4-byte loads) instead of 16-byte row packs
   int multi_mode;      // PB_OPT_MULTI_ITER: 0 auto, -1 never, 1 force (even when contexts share a device)

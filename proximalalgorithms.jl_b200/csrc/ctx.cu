@@ -153,6 +153,10 @@ extern "C" int pb_ctx_set_option(pb_ctx* c, int option, int value) {
       PB_REQUIRE(value >= -1 && value <= 32, "persistent mode must be -1, 0 or 1..32");
       c->persist_mode = value;
       return PB_OK;
+    case PB_OPT_LSQ_FISTA:
+      PB_REQUIRE(value >= -1 && value <= 1, "single-sweep FISTA mode must be -1, 0 or 1");
+      c->lsq_fista = value;
+      return PB_OK;
     case PB_OPT_LSQ_FUSED:
       PB_REQUIRE(value >= -1 && value <= 8, "fused least-squares mode must be -1, 0 or 1..8");
       c->lsq_fused = value;

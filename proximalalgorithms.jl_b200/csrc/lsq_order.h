@@ -26,6 +26,9 @@ static inline PbLsqOrder pb_lsq_order(size_t elt, int64_t nblk, int64_t mb, int6
   int64_t chunk_cols = (nb + 63) / 64;
   if (chunk_cols < PB_GEMV_CL * PB_GEMV_UNROLL) chunk_cols = PB_GEMV_CL * PB_GEMV_UNROLL;
   if (chunk_cols > 4096) chunk_cols = 4096;
+  // a multiple of 4 columns (the clamps already are): chunk boundaries then never cut a 16-byte pack of the n-vectors, which lets
+  // lsq_fista.cu run the fused step -- whose float reductions are grouped per pack -- on the columns of one chunk
+  chunk_cols = (chunk_cols + 3) & ~(int64_t)3;
   o.chunk_cols = chunk_cols;
   o.nchunk = nb > 0 ? (nb + chunk_cols - 1) / chunk_cols : 1;
   const int64_t npk = mb / VEC;

@@ -17,6 +17,10 @@
 #include "common.cuh"
 #include "solve_scalar.h"
 
+bool pb_bd_fista_eligible(const pb_ctx* ctx, int dtype, const pb_smooth* f, const pb_prox* g, const void* x, const void* z_prev, const void* grad,
+                          const void* z, const void* x_next);   // lsq_fista.cu
+int pb_bd_fista_step(pb_ctx* ctx, int dtype, const pb_smooth* f, const pb_prox* g, double gamma, double beta, const void* x, const void* z_prev,
+                     void* grad, void* z, void* x_next);
 bool pb_multi_eligible(const pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o, const void* x_next);   // step_multi.cu
 int pb_multi_run(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, const pb_prox* g, const pb_solve_opts* o, void* const X[3],
                  void* const Z[3], int64_t* k_out, double comb[4], float* kernel_ms);
@@ -284,6 +288,8 @@ struct Solver {
       rc = run_ffb_multi(out);
       if (rc != PB_EUNSUPPORTED) return rc;
     }
+    // block-diagonal least squares + fixed stepsize: ONE sweep of A per iteration (lsq_fista.cu), same results
+    if (fast && !adaptive && x_next && n > 0 && pb_bd_fista_eligible(ctx, dtype, f, g, x, z_prev, grad, z, x_next)) return run_ffb_bd_fista(out, seq);
     if (fast) {
       if ((rc = pb_copy(ctx, z_prev, x, (size_t)n * (dtype == PB_F32 ? 4 : 8)))) return rc;     // z_prev = copy(x)
       if (!adaptive) {
@@ -414,6 +420,31 @@ struct Solver {
   }
 
   int eval_f_to(const void* v, void* grad_out) { return eval_f(v, grad_out); }
+
+  // Fixed-stepsize FFB on a block-diagonal least-squares term with one sweep of A per iteration (csrc/lsq_fista.cu): the kernel of iteration
+  // k computes grad f(x_k) from r_k = A x_k - b, the fused step, and the partial products of A x_{k+1}; its combine leaves r_{k+1} in f->r and
+  // ||r_{k+1}||^2 in AUX, i.e. the value of the NEXT point, which is shifted here.  On entry eval_f(x, grad) of the init has left r_1 and AUX.
+  int run_ffb_bd_fista(pb_solve_result* out, Nesterov<R>& seq) {
+    int rc;
+    if ((rc = pb_copy(ctx, z_prev, x, (size_t)n * (dtype == PB_F32 ? 4 : 8)))) return rc;     // z_prev = copy(x)
+    Comb c0;
+    if ((rc = read_comb(ctx, &c0))) return rc;
+    R f_cur = f_value(c0);
+    int64_t k = 1;
+    for (;;) {
+      const R beta = seq.next(gamma);
+      if ((rc = pb_bd_fista_step(ctx, dtype, f, g, (double)gamma, (double)beta, x, z_prev, grad, z, x_next))) return rc;
+      if ((rc = read_comb(ctx, &sc))) return rc;
+      f_x = f_cur;
+      g_z = g_value(sc);
+      if (k >= o->maxit || stop()) break;                       // src/ProximalAlgorithms.jl:117
+      f_cur = f_value(sc);                                      // AUX = ||A x_{k+1} - b||^2
+      void* t = x; x = x_next; x_next = t;                      // fast_forward_backward.jl:135, computed by the fused pass
+      t = z_prev; z_prev = z; z = t;                            // :136
+      ++k;
+    }
+    return finish(out, k);
+  }
 
   // Fixed-stepsize FFB, f = <c, .> or SquaredDistance: iterations 1 .. k inside ONE kernel (csrc/step_multi.cu).  The rings are laid
   // out so that iteration 1 reads the caller's x (= copy(x0)) and z_prev (= copy(x)): X[1] = x, Z[0] = z_prev.

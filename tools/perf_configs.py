@@ -17,7 +17,7 @@ from proxb200 import _lib as L  # noqa: E402
 from proxb200.host import Context, DeviceExchangeComm, ptr  # noqa: E402
 from tune_step import timeit  # noqa: E402
 
-PEAK = 6567.4
+PEAK = 6451.8   # MEASURED_PEAKS.json hbm_gbs of this pool
 
 
 def main():
@@ -48,21 +48,26 @@ def main():
     comm = DeviceExchangeComm(ctx)
     try:
         K = 200
-        solver = pa.FastForwardBackward(maxit=K, tol=-1.0)
         x0 = torch.zeros_like(xt)
-        solver(x0=x0, f=f, g=pa.NormL1(lam), Lf=1.05 * Lhat, comm=comm)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        z, it = solver(x0=x0, f=f, g=pa.NormL1(lam), Lf=1.05 * Lhat, comm=comm)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        st = solver.last_state
-        bytes_iter = 2 * A.numel() * 4 + 5 * 4 * xt.numel() + 4 * 4 * b.numel()
-        out["config1_blockdiag_fista_n1e7"] = dict(iterations=it, seconds=dt, it_per_s=it / dt, ms_per_iteration=1e3 * dt / it,
-                                                   algorithmic_bytes_per_iteration=bytes_iter, gbs=bytes_iter * it / dt / 1e9,
-                                                   frac_of_measured_peak=bytes_iter * it / dt / 1e9 / PEAK, Lhat=Lhat, lam=lam,
-                                                   final_res_inf_over_gamma=float(st.res_norm_inf / st.gamma), nnz=int((z != 0).sum()))
-        print(out["config1_blockdiag_fista_n1e7"], flush=True)
+        for mode, key in ((-1, "config1_blockdiag_fista_n1e7_two_sweeps"), (0, "config1_blockdiag_fista_n1e7")):
+            # mode -1: residual + gradient + fused step kernels (A swept twice per iteration); 0 = auto: csrc/lsq_fista.cu (A swept once)
+            L.check(ctx.lib.pb_ctx_set_option(ctx.h, L.PB_OPT_LSQ_FISTA, mode))
+            solver = pa.FastForwardBackward(maxit=K, tol=-1.0)
+            solver(x0=x0, f=f, g=pa.NormL1(lam), Lf=1.05 * Lhat, comm=comm)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            z, it = solver(x0=x0, f=f, g=pa.NormL1(lam), Lf=1.05 * Lhat, comm=comm)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            st = solver.last_state
+            sweeps = 2 if mode < 0 else 1
+            bytes_iter = sweeps * A.numel() * 4 + 5 * 4 * xt.numel() + 4 * 4 * b.numel()
+            out[key] = dict(iterations=it, seconds=dt, it_per_s=it / dt, ms_per_iteration=1e3 * dt / it, sweeps_of_A_per_iteration=sweeps,
+                            algorithmic_bytes_per_iteration=bytes_iter, gbs=bytes_iter * it / dt / 1e9,
+                            frac_of_measured_peak=bytes_iter * it / dt / 1e9 / PEAK, Lhat=Lhat, lam=lam,
+                            final_res_inf_over_gamma=float(st.res_norm_inf / st.gamma), nnz=int((z != 0).sum()), parity=dict(solver.last_parity))
+            print(key, out[key], flush=True)
+        L.check(ctx.lib.pb_ctx_set_option(ctx.h, L.PB_OPT_LSQ_FISTA, 0))
         # same problem, adaptive (backtracking) FISTA to tol 1e-4: a real solve
         t0 = time.perf_counter()
         z2, it2 = pa.FastForwardBackward(maxit=3000, tol=1e-4)(x0=x0, f=f, g=pa.NormL1(lam), comm=comm)
