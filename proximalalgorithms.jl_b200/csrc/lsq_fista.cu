@@ -23,7 +23,7 @@
 #include "tma.cuh"
 
 #define LF_BLOCK 256
-#define LF_STAGES 3
+#define LF_MAX_STAGES 8
 
 struct LfParams {
   const void* A;
@@ -36,7 +36,7 @@ struct LfParams {
   void* partial;            // [nchunk][nblk][mb] chunk partials of A x_next
   double* unit_red;         // [units][8]: gsum (hi, lo), res_sq (hi, lo), gdr (hi, lo), res_inf
   int64_t nblk, mb, nb, chunk_cols;
-  int nchunk, t_lpc, t_kp, tile_cols;
+  int nchunk, t_lpc, t_kp, tile_cols, stages;
   int prox_kind;
   double gamma, beta, pa, pb;       // prox parameters already combined in the element type (launch_step_prox convention)
 };
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(LF_BLOCK, 2) k_bd_fista(LfParams p) {
   constexpr bool COMP = sizeof(T) == 8;
   constexpr int VEC = 16 / sizeof(T);
   extern __shared__ __align__(128) unsigned char lf_smem[];
-  __shared__ uint64_t full[LF_STAGES];
+  __shared__ uint64_t full[LF_MAX_STAGES];
   __shared__ uint64_t aux_full;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t mb = p.mb, nb = p.nb;
@@ -61,12 +61,13 @@ __global__ void __launch_bounds__(LF_BLOCK, 2) k_bd_fista(LfParams p) {
   const int ntile = (ncols + TC - 1) / TC;
   const int64_t cc4 = (p.chunk_cols + 3) & ~(int64_t)3;
 
-  T* ring = reinterpret_cast<T*>(lf_smem);                     // [LF_STAGES][TC][mb]
-  T* xs = ring + (size_t)LF_STAGES * TC * mb;                  // x chunk
+  const int S = p.stages;
+  T* ring = reinterpret_cast<T*>(lf_smem);                     // [S][TC][mb]
+  T* xs = ring + (size_t)S * TC * mb;                          // x chunk
   T* zps = xs + cc4;                                           // z_prev chunk
-  T* g_sm = zps + cc4;                                         // [TC] grad of the tile
-  T* xn_sm = g_sm + TC;                                        // [TC] x_next of the tile
-  Pack<T, VEC>* lp = reinterpret_cast<Pack<T, VEC>*>(xn_sm + TC);   // [4][npk] lane partials
+  T* g_sm = zps + cc4;                                         // [TC] grad of the tile in phase A / B
+  T* xn_sm = g_sm + TC;                                        // [2][TC] x_next of tile t (C reads) and tile t + 1 (B writes)
+  Pack<T, VEC>* lp = reinterpret_cast<Pack<T, VEC>*>(xn_sm + 2 * TC);   // [4][npk] lane partials
 
   const T* __restrict__ A = static_cast<const T*>(p.A);
   const T* __restrict__ src = A + ((int64_t)k * nb + c0) * mb;
@@ -74,21 +75,21 @@ __global__ void __launch_bounds__(LF_BLOCK, 2) k_bd_fista(LfParams p) {
   const T gamma = (T)p.gamma, beta = (T)p.beta, pa = (T)p.pa, pb = (T)p.pb;
 
   auto issue = [&](int t) {                                    // thread 0
-    const int s = t % LF_STAGES;
+    const int s = t % S;
     const int tc = ncols - t * TC < TC ? ncols - t * TC : TC;
     const uint32_t bytes = (uint32_t)tc * col_bytes;
     mbar_expect_tx(&full[s], bytes);
     bulk_g2s(ring + (size_t)s * TC * mb, src + (int64_t)t * TC * mb, bytes, &full[s]);
   };
   if (tid == 0) {
-    for (int s = 0; s < LF_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     mbar_init(&aux_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t vb = (uint32_t)ncols * (uint32_t)sizeof(T);
     mbar_expect_tx(&aux_full, 2 * vb);
     bulk_g2s(xs, static_cast<const T*>(p.x) + j0, vb, &aux_full);
     bulk_g2s(zps, static_cast<const T*>(p.z_prev) + j0, vb, &aux_full);
-    const int pre = ntile < LF_STAGES ? ntile : LF_STAGES;
+    const int pre = ntile < S ? ntile : S;
     for (int t = 0; t < pre; ++t) issue(t);
   }
   // r_k of this block: the packs this lane multiplies with (k_gemv_t_sub keeps them in registers for the whole chunk too)
@@ -120,12 +121,17 @@ __global__ void __launch_bounds__(LF_BLOCK, 2) k_bd_fista(LfParams p) {
   T* __restrict__ zo = static_cast<T*>(p.z) + j0;
   T* __restrict__ xo = static_cast<T*>(p.x_next) + j0;
 
-  for (int t = 0; t < ntile; ++t) {
-    const int s = t % LF_STAGES;
-    mbar_wait(&full[s], (uint32_t)((t / LF_STAGES) & 1));
+  // Software pipeline over the tiles, two barriers per tile:
+  //     [ A(t+1): all warps ]  barrier  [ B(t+1): the last TC/VEC threads  ||  C(t): the first 4*npk threads ]  barrier, refill stage of tile t
+  // A = gradient of the tile's columns, B = fused step on them, C = their contribution to the chunk partial of A x_next.
+  const int nb_thr = TC / VEC;                                  // threads of phase B, taken from the END of the CTA (C uses the beginning)
+  const bool b_thread = tid >= LF_BLOCK - nb_thr;
+  const int bt = tid - (LF_BLOCK - nb_thr);
+  auto phase_A = [&](int t) {
+    const int s = t % S;
+    mbar_wait(&full[s], (uint32_t)((t / S) & 1));
     const T* tile = ring + (size_t)s * TC * mb;
     const int tc = ncols - t * TC < TC ? ncols - t * TC : TC;
-    // ---- A: grad of the tile's columns
     for (int cb = warp * cpw; cb < tc; cb += (LF_BLOCK / 32) * cpw) {
       const int col = cb + colw;
       const bool live = col < tc;
@@ -143,13 +149,14 @@ __global__ void __launch_bounds__(LF_BLOCK, 2) k_bd_fista(LfParams p) {
       for (int off = lpc >> 1; off > 0; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
       if (live && sub == 0) g_sm[col] = g;
     }
-    __syncthreads();
-    // ---- B: fused step on the tile's columns, one 16-byte pack per thread
-    if (tid * VEC < tc) {
-      const int jl = t * TC + tid * VEC;                        // offset inside the chunk
+  };
+  auto phase_B = [&](int t) {                                   // b-threads only: one 16-byte pack of columns each
+    const int tc = ncols - t * TC < TC ? ncols - t * TC : TC;
+    if (bt * VEC < tc) {
+      const int jl = t * TC + bt * VEC;                         // offset inside the chunk
       const Pack<T, VEC> xq = *reinterpret_cast<const Pack<T, VEC>*>(xs + jl);
       const Pack<T, VEC> zq = *reinterpret_cast<const Pack<T, VEC>*>(zps + jl);
-      const Pack<T, VEC> gq = *reinterpret_cast<const Pack<T, VEC>*>(g_sm + tid * VEC);
+      const Pack<T, VEC> gq = *reinterpret_cast<const Pack<T, VEC>*>(g_sm + bt * VEC);
       Pack<T, VEC> zn, xn;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
@@ -157,24 +164,35 @@ __global__ void __launch_bounds__(LF_BLOCK, 2) k_bd_fista(LfParams p) {
         StepElem<T, PROX, true>::template run<COMP>(xq.v[e], gq.v[e], zq.v[e], pa, pb, gamma, beta, yv, zn.v[e], rvv, xn.v[e], COMP ? acc : pkacc);
       }
       if constexpr (!COMP) fold_pack<PROX>(acc, pkacc);
-      *reinterpret_cast<Pack<T, VEC>*>(xn_sm + tid * VEC) = xn;
+      *reinterpret_cast<Pack<T, VEC>*>(xn_sm + (t & 1) * TC + bt * VEC) = xn;
       *reinterpret_cast<Pack<T, VEC>*>(go + jl) = gq;
       *reinterpret_cast<Pack<T, VEC>*>(zo + jl) = zn;
       *reinterpret_cast<Pack<T, VEC>*>(xo + jl) = xn;
     }
-    __syncthreads();
-    // ---- C: the tile's contribution to the chunk partial of A x_next
-    if (n_active) {
+  };
+  auto phase_C = [&](int t) {                                   // n_active threads only
+    const T* tile = ring + (size_t)(t % S) * TC * mb;
+    const T* xn = xn_sm + (t & 1) * TC;
+    const int tc = ncols - t * TC < TC ? ncols - t * TC : TC;
 #pragma unroll 4
-      for (int jj = cl; jj < tc; jj += 4) {
-        const Pack<T, VEC> a = *reinterpret_cast<const Pack<T, VEC>*>(tile + (size_t)jj * mb + pk * VEC);
-        const T xv = xn_sm[jj];
+    for (int jj = cl; jj < tc; jj += 4) {
+      const Pack<T, VEC> a = *reinterpret_cast<const Pack<T, VEC>*>(tile + (size_t)jj * mb + pk * VEC);
+      const T xv = xn[jj];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) nacc.v[e] = fma(a.v[e], xv, nacc.v[e]);
-      }
+      for (int e = 0; e < VEC; ++e) nacc.v[e] = fma(a.v[e], xv, nacc.v[e]);
     }
-    __syncthreads();                                            // stage s and g_sm / xn_sm are free again
-    if (tid == 0 && t + LF_STAGES < ntile) issue(t + LF_STAGES);
+  };
+  phase_A(0);
+  __syncthreads();
+  if (b_thread) phase_B(0);
+  __syncthreads();
+  for (int t = 0; t < ntile; ++t) {
+    if (t + 1 < ntile) phase_A(t + 1);
+    __syncthreads();                                            // g_sm of tile t + 1 is complete (B(t) read the previous one before the last barrier)
+    if (b_thread && t + 1 < ntile) phase_B(t + 1);
+    if (n_active) phase_C(t);
+    __syncthreads();                                            // tile t's stage and xn_sm[t & 1] are free
+    if (tid == 0 && t + S < ntile) issue(t + S);
   }
   // ---- chunk partial: lanes added ((l0 + l1) + l2) + l3
   if (n_active) lp[cl * npk + pk] = nacc;
@@ -245,7 +263,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_bd_fista_combine(const T* __restri
 // ---------------------------------------------------------------------------------------------------------------------
 struct LfPlan {
   PbLsqOrder ord;
-  int tile_cols;
+  int tile_cols, stages;
   size_t smem;
 };
 
@@ -266,12 +284,18 @@ static bool lf_plan(const pb_ctx* ctx, const pb_smooth* f, const pb_prox* g, con
     return false;
   // worth it only when A does not live in L2 anyway
   if (ctx->lsq_fista == 0 && (double)f->nblk * (double)mb * (double)nb * sizeof(T) < 64.0 * 1024 * 1024) return false;
-  int tc = 64;
-  while (tc >= 16 && (size_t)tc * mb * sizeof(T) > 26 * 1024) tc >>= 1;
-  if (tc < 16 || tc / VEC > LF_BLOCK) return false;
+  // small tiles, deep ring: two tiles are in use (A on t + 1, C on t), the rest of the ring is prefetch
+  int tc = 32;
+  while (tc >= 8 && (size_t)tc * mb * sizeof(T) > 16 * 1024) tc >>= 1;
+  if (tc < 8 || tc % VEC != 0 || tc / VEC > LF_BLOCK) return false;   // (a thread may own both a B pack and a C row pack: it does B, then C)
   const size_t cc4 = ((size_t)plan->ord.chunk_cols + 3) & ~(size_t)3;
+  const size_t tile_bytes = (size_t)tc * mb * sizeof(T);
+  int stages = (int)((size_t)80 * 1024 / tile_bytes);
+  if (stages > LF_MAX_STAGES) stages = LF_MAX_STAGES;
+  if (stages < 4) return false;
   plan->tile_cols = tc;
-  plan->smem = ((size_t)LF_STAGES * tc * mb + 2 * cc4 + 2 * tc) * sizeof(T) + (size_t)4 * npk * 16 + 128;
+  plan->stages = stages;
+  plan->smem = (size_t)stages * tile_bytes + (2 * cc4 + 3 * tc) * sizeof(T) + (size_t)4 * npk * 16 + 128;
   return plan->smem <= 110 * 1024;
 }
 
@@ -330,6 +354,7 @@ static int lf_run(pb_ctx* ctx, const pb_smooth* f, const pb_prox* g, double gamm
   p.t_lpc = plan.ord.t_lpc;
   p.t_kp = plan.ord.t_kp;
   p.tile_cols = plan.tile_cols;
+  p.stages = plan.stages;
   p.prox_kind = g->kind;
   p.gamma = (double)(T)gamma;
   p.beta = (double)(T)beta;
