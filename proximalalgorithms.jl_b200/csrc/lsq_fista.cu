@@ -16,13 +16,15 @@
 // Every arithmetic order is that of the separate kernels, so iterates, scalars and iteration counts are bit-identical to
 // residual + gradient + K2 (tests/test_gpu_lsq.py, tests/test_gpu_solvers.py); HBM traffic per iteration drops from 2 |A| + 5 n
 // to |A| + 5 n elements.
+#include <stdlib.h>
 #include <string.h>
 
 #include "lsq_order.h"
 #include "step_common.cuh"
 #include "tma.cuh"
 
-#define LF_MAX_STAGES 8
+#define LF_BLOCK 256
+#define LF_STAGES 3
 
 struct LfParams {
   const void* A;
@@ -35,21 +37,18 @@ struct LfParams {
   void* partial;            // [nchunk][nblk][mb] chunk partials of A x_next
   double* unit_red;         // [units][8]: gsum (hi, lo), res_sq (hi, lo), gdr (hi, lo), res_inf
   int64_t nblk, mb, nb, chunk_cols;
-  int nchunk, t_lpc, t_kp, tile_cols, stages;
+  int nchunk, t_lpc, t_kp, tile_cols;
   int prox_kind;
   double gamma, beta, pa, pb;       // prox parameters already combined in the element type (launch_step_prox convention)
 };
 
-// NT threads per CTA, MINB CTAs per SM.  Occupancy matters more than anything else here: every phase of a tile is a short dependent
-// chain (ncu on the first version, 2 CTAs x 256 threads per SM: 25 % warps active, the stall samples split between bar.sync, fixed-latency
-// dependencies and shared-memory latency, almost none on global memory), so the shape is small CTAs with a small ring and many of them
-// per SM; the TMA ring keeps (S - 2) tiles per CTA in flight.
-template <typename T, int PROX, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_bd_fista(LfParams p) {
+template <typename T, int PROX>
+__global__ void __launch_bounds__(LF_BLOCK, 2) k_bd_fista(LfParams p) {
   constexpr bool COMP = sizeof(T) == 8;
   constexpr int VEC = 16 / sizeof(T);
   extern __shared__ __align__(128) unsigned char lf_smem[];
-  __shared__ uint64_t full[LF_MAX_STAGES];
+  __shared__ uint64_t full[LF_STAGES];
+  __shared__ uint64_t aux_full;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t mb = p.mb, nb = p.nb;
   const int npk = (int)(mb / VEC);
@@ -61,30 +60,37 @@ __global__ void __launch_bounds__(NT, MINB) k_bd_fista(LfParams p) {
   if (c1 > nb) c1 = nb;
   const int ncols = (int)(c1 - c0);
   const int ntile = (ncols + TC - 1) / TC;
+  const int64_t cc4 = (p.chunk_cols + 3) & ~(int64_t)3;
 
-  const int S = p.stages;
-  const size_t tile_elts = (size_t)TC * mb;
-  T* ring = reinterpret_cast<T*>(lf_smem);                     // [S][TC][mb]
-  T* g_sm = ring + (size_t)S * tile_elts;                      // [TC] grad of the tile in phase A / B
-  T* xn_sm = g_sm + TC;                                        // [2][TC] x_next of tile t (C reads) and tile t + 1 (B writes)
-  Pack<T, VEC>* lp = reinterpret_cast<Pack<T, VEC>*>(xn_sm + 2 * TC);   // [4][npk] lane partials
+  T* ring = reinterpret_cast<T*>(lf_smem);                     // [LF_STAGES][TC][mb]
+  T* xs = ring + (size_t)LF_STAGES * TC * mb;                  // x chunk
+  T* zps = xs + cc4;                                           // z_prev chunk
+  T* g_sm = zps + cc4;                                         // [TC] grad of the tile
+  T* xn_sm = g_sm + TC;                                        // [TC] x_next of the tile
+  Pack<T, VEC>* lp = reinterpret_cast<Pack<T, VEC>*>(xn_sm + TC);   // [4][npk] lane partials
 
   const T* __restrict__ A = static_cast<const T*>(p.A);
   const T* __restrict__ src = A + ((int64_t)k * nb + c0) * mb;
   const int64_t j0 = (int64_t)k * nb + c0;                     // first element of this unit in the n-vectors
   const T gamma = (T)p.gamma, beta = (T)p.beta, pa = (T)p.pa, pb = (T)p.pb;
 
-  auto issue = [&](int t, int s) {                             // thread 0: bulk-load tile t into stage s
+  auto issue = [&](int t) {                                    // thread 0
+    const int s = t % LF_STAGES;
     const int tc = ncols - t * TC < TC ? ncols - t * TC : TC;
     const uint32_t bytes = (uint32_t)tc * col_bytes;
     mbar_expect_tx(&full[s], bytes);
-    bulk_g2s(ring + (size_t)s * tile_elts, src + (int64_t)t * tile_elts, bytes, &full[s]);
+    bulk_g2s(ring + (size_t)s * TC * mb, src + (int64_t)t * TC * mb, bytes, &full[s]);
   };
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < LF_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_init(&aux_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const int pre = ntile < S ? ntile : S;
-    for (int t = 0; t < pre; ++t) issue(t, t);
+    const uint32_t vb = (uint32_t)ncols * (uint32_t)sizeof(T);
+    mbar_expect_tx(&aux_full, 2 * vb);
+    bulk_g2s(xs, static_cast<const T*>(p.x) + j0, vb, &aux_full);
+    bulk_g2s(zps, static_cast<const T*>(p.z_prev) + j0, vb, &aux_full);
+    const int pre = ntile < LF_STAGES ? ntile : LF_STAGES;
+    for (int t = 0; t < pre; ++t) issue(t);
   }
   // r_k of this block: the packs this lane multiplies with (k_gemv_t_sub keeps them in registers for the whole chunk too)
   const int lpc = p.t_lpc, kp = p.t_kp;
@@ -100,43 +106,28 @@ __global__ void __launch_bounds__(NT, MINB) k_bd_fista(LfParams p) {
 #pragma unroll
       for (int e = 0; e < VEC; ++e) rv[q].v[e] = T(0);
   }
+  __syncthreads();                                             // mbarrier inits visible
+  mbar_wait(&aux_full, 0);
+
   const bool n_active = tid < npk * 4;
   const int pk = n_active ? tid % npk : 0, cl = n_active ? tid / npk : 0;
   Pack<T, VEC> nacc;
 #pragma unroll
   for (int e = 0; e < VEC; ++e) nacc.v[e] = T(0);
-  Acc<3, 1> acc, pkacc;                                        // step reductions of the packs this thread owns (phase B threads)
+  Acc<3, 1> acc, pkacc;                                        // step reductions of the packs this thread owns (tid < TC / VEC)
   acc.clear();
   pkacc.clear();
-  const T* __restrict__ xin = static_cast<const T*>(p.x) + j0;
-  const T* __restrict__ zin = static_cast<const T*>(p.z_prev) + j0;
   T* __restrict__ go = static_cast<T*>(p.grad) + j0;
   T* __restrict__ zo = static_cast<T*>(p.z) + j0;
   T* __restrict__ xo = static_cast<T*>(p.x_next) + j0;
-  // phase B threads: the last TC / VEC threads of the CTA, one 16-byte pack of columns each; x and z_prev of the NEXT tile are
-  // fetched (16-byte streaming loads) while the current one is processed
-  const int nb_thr = TC / VEC;
-  const bool b_thread = tid >= NT - nb_thr;
-  const int bt = tid - (NT - nb_thr);
-  Pack<T, VEC> xq_n, zq_n;
-  auto fetch_xz = [&](int t) {
-    const int jl = t * TC + bt * VEC;
-    if (t < ntile && jl < ncols) {
-      xq_n = ld_pack<T, VEC, true>(xin + jl);
-      zq_n = ld_pack<T, VEC, true>(zin + jl);
-    }
-  };
-  if (b_thread) fetch_xz(0);
-  __syncthreads();                                             // mbarrier inits visible
 
-  // Software pipeline over the tiles, two barriers per tile:
-  //     [ A(t+1): all warps ]  barrier  [ B(t+1): phase B threads  ||  C(t): the first 4*npk threads ]  barrier, refill the stage of tile t
-  // A = gradient of the tile's columns, B = fused step on them, C = their contribution to the chunk partial of A x_next.
-  auto phase_A = [&](int t, int s, uint32_t par) {
-    mbar_wait(&full[s], par);
-    const T* tile = ring + (size_t)s * tile_elts;
+  for (int t = 0; t < ntile; ++t) {
+    const int s = t % LF_STAGES;
+    mbar_wait(&full[s], (uint32_t)((t / LF_STAGES) & 1));
+    const T* tile = ring + (size_t)s * TC * mb;
     const int tc = ncols - t * TC < TC ? ncols - t * TC : TC;
-    for (int cb = warp * cpw; cb < tc; cb += (NT / 32) * cpw) {
+    // ---- A: grad of the tile's columns
+    for (int cb = warp * cpw; cb < tc; cb += (LF_BLOCK / 32) * cpw) {
       const int col = cb + colw;
       const bool live = col < tc;
       const T* a = tile + (size_t)(live ? col : 0) * mb;
@@ -153,14 +144,13 @@ __global__ void __launch_bounds__(NT, MINB) k_bd_fista(LfParams p) {
       for (int off = lpc >> 1; off > 0; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
       if (live && sub == 0) g_sm[col] = g;
     }
-  };
-  auto phase_B = [&](int t) {                                   // b-threads only
-    const int tc = ncols - t * TC < TC ? ncols - t * TC : TC;
-    const Pack<T, VEC> xq = xq_n, zq = zq_n;
-    fetch_xz(t + 1);
-    if (bt * VEC < tc) {
-      const int jl = t * TC + bt * VEC;                         // offset inside the chunk
-      const Pack<T, VEC> gq = *reinterpret_cast<const Pack<T, VEC>*>(g_sm + bt * VEC);
+    __syncthreads();
+    // ---- B: fused step on the tile's columns, one 16-byte pack per thread
+    if (tid * VEC < tc) {
+      const int jl = t * TC + tid * VEC;                        // offset inside the chunk
+      const Pack<T, VEC> xq = *reinterpret_cast<const Pack<T, VEC>*>(xs + jl);
+      const Pack<T, VEC> zq = *reinterpret_cast<const Pack<T, VEC>*>(zps + jl);
+      const Pack<T, VEC> gq = *reinterpret_cast<const Pack<T, VEC>*>(g_sm + tid * VEC);
       Pack<T, VEC> zn, xn;
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
@@ -168,45 +158,25 @@ __global__ void __launch_bounds__(NT, MINB) k_bd_fista(LfParams p) {
         StepElem<T, PROX, true>::template run<COMP>(xq.v[e], gq.v[e], zq.v[e], pa, pb, gamma, beta, yv, zn.v[e], rvv, xn.v[e], COMP ? acc : pkacc);
       }
       if constexpr (!COMP) fold_pack<PROX>(acc, pkacc);
-      *reinterpret_cast<Pack<T, VEC>*>(xn_sm + (t & 1) * TC + bt * VEC) = xn;
-      st_pack<T, VEC, true>(go + jl, gq);
-      st_pack<T, VEC, true>(zo + jl, zn);
-      st_pack<T, VEC, true>(xo + jl, xn);
+      *reinterpret_cast<Pack<T, VEC>*>(xn_sm + tid * VEC) = xn;
+      *reinterpret_cast<Pack<T, VEC>*>(go + jl) = gq;
+      *reinterpret_cast<Pack<T, VEC>*>(zo + jl) = zn;
+      *reinterpret_cast<Pack<T, VEC>*>(xo + jl) = xn;
     }
-  };
-  auto phase_C = [&](int t, int s) {                            // n_active threads only
-    const T* tile = ring + (size_t)s * tile_elts;
-    const T* xn = xn_sm + (t & 1) * TC;
-    const int tc = ncols - t * TC < TC ? ncols - t * TC : TC;
+    __syncthreads();
+    // ---- C: the tile's contribution to the chunk partial of A x_next
+    if (n_active) {
 #pragma unroll 4
-    for (int jj = cl; jj < tc; jj += 4) {
-      const Pack<T, VEC> a = *reinterpret_cast<const Pack<T, VEC>*>(tile + (size_t)jj * mb + pk * VEC);
-      const T xv = xn[jj];
+      for (int jj = cl; jj < tc; jj += 4) {
+        const Pack<T, VEC> a = *reinterpret_cast<const Pack<T, VEC>*>(tile + (size_t)jj * mb + pk * VEC);
+        const T xv = xn_sm[jj];
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) nacc.v[e] = fma(a.v[e], xv, nacc.v[e]);
+        for (int e = 0; e < VEC; ++e) nacc.v[e] = fma(a.v[e], xv, nacc.v[e]);
+      }
     }
-  };
-  int s_cur = 0, s_nxt = 1 % S;                                // stage of tile t / t + 1
-  uint32_t par_cur = 0, par_nxt = S == 1 ? 1u : 0u;             // their mbarrier parities
-  phase_A(0, 0, 0);
-  __syncthreads();
-  if (b_thread) phase_B(0);
-  __syncthreads();
-  for (int t = 0; t < ntile; ++t) {
-    if (t + 1 < ntile) phase_A(t + 1, s_nxt, par_nxt);
-    __syncthreads();                                            // g_sm of tile t + 1 is complete (B(t) read the previous one before the last barrier)
-    if (b_thread && t + 1 < ntile) phase_B(t + 1);
-    if (n_active) phase_C(t, s_cur);
-    __syncthreads();                                            // tile t's stage and xn_sm[t & 1] are free
-    if (tid == 0 && t + S < ntile) issue(t + S, s_cur);
-    s_cur = s_nxt;
-    par_cur = par_nxt;
-    if (++s_nxt == S) {
-      s_nxt = 0;
-      par_nxt ^= 1u;
-    }
+    __syncthreads();                                            // stage s and g_sm / xn_sm are free again
+    if (tid == 0 && t + LF_STAGES < ntile) issue(t + LF_STAGES);
   }
-  (void)par_cur;
   // ---- chunk partial: lanes added ((l0 + l1) + l2) + l3
   if (n_active) lp[cl * npk + pk] = nacc;
   __syncthreads();
@@ -219,7 +189,7 @@ __global__ void __launch_bounds__(NT, MINB) k_bd_fista(LfParams p) {
     *reinterpret_cast<Pack<T, VEC>*>(static_cast<T*>(p.partial) + ((int64_t)c * p.nblk + k) * mb + tid * VEC) = s_;
   }
   // ---- the unit's step reductions
-  block_reduce<3, 1, NT>(acc);
+  block_reduce<3, 1, LF_BLOCK>(acc);
   if (tid == 0) {
     double* o = p.unit_red + ((size_t)k * p.nchunk + c) * 8;
     o[0] = acc.s[0].hi;
@@ -276,7 +246,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_bd_fista_combine(const T* __restri
 // ---------------------------------------------------------------------------------------------------------------------
 struct LfPlan {
   PbLsqOrder ord;
-  int tile_cols, stages, nt;
+  int tile_cols;
   size_t smem;
 };
 
@@ -290,31 +260,26 @@ static bool lf_plan(const pb_ctx* ctx, const pb_smooth* f, const pb_prox* g, con
   if (g->kind == PB_PROX_BOX && (g->v0 || g->v1)) return false;
   const int64_t mb = f->mb, nb = f->nb, npk = mb / VEC;
   plan->ord = pb_lsq_order(sizeof(T), f->nblk, mb, nb, mb, mb * nb, f->A, f->r);
-  if (plan->ord.n_sub || !plan->ord.t_sub || mb % VEC != 0 || nb % VEC != 0 || plan->ord.chunk_cols % VEC != 0 || npk * 4 > 256) return false;
+  if (plan->ord.n_sub || !plan->ord.t_sub || mb % VEC != 0 || nb % VEC != 0 || plan->ord.chunk_cols % VEC != 0 || npk * 4 > LF_BLOCK) return false;
   if (f->nblk > 65535 || plan->ord.nchunk > 0x7fffffff) return false;
   if (!pb_aligned16(f->A) || !pb_aligned16(f->r) || !pb_aligned16(x) || !pb_aligned16(z_prev) || !pb_aligned16(grad) || !pb_aligned16(z) ||
       !pb_aligned16(x_next))
     return false;
   // worth it only when A does not live in L2 anyway
   if (ctx->lsq_fista == 0 && (double)f->nblk * (double)mb * (double)nb * sizeof(T) < 64.0 * 1024 * 1024) return false;
-  // CTA shape: 128 threads when the 4 * npk threads of phase C fit (columns of <= 32 packs), else 256; tile = one sweep of phase A
-  // (warps x columns-per-warp), ring of up to 6 tiles: two in use (A on t + 1, C on t), the rest prefetch
-  const int nt = npk * 4 <= 128 ? 128 : 256;
-  if (npk * 4 > nt) return false;
-  const int cpw = 32 / plan->ord.t_lpc;
-  int tc = (nt / 32) * cpw;
-  if (tc > 64) tc = 64;
-  while (tc >= 8 && (size_t)tc * mb * sizeof(T) > 8 * 1024) tc >>= 1;
-  if (tc < 8 || tc % 4 != 0 || tc / VEC > nt) return false;
-  const size_t tile_bytes = (size_t)tc * mb * sizeof(T);
-  int stages = (int)((size_t)40 * 1024 / tile_bytes);
-  if (stages > 6) stages = 6;
-  if (stages < 3) return false;
+  int tc = 64;
+  size_t tile_cap = 26 * 1024, smem_cap = 110 * 1024;
+  if (const char* e = getenv("PROXB200_LF_TC")) {       // tuning hook (tools/tune_lsq_fista.sh): tile columns; large tiles take one CTA per SM
+    tc = atoi(e);
+    tile_cap = 64 * 1024;
+    smem_cap = 200 * 1024;
+  }
+  while (tc >= 16 && (size_t)tc * mb * sizeof(T) > tile_cap) tc >>= 1;
+  if (tc < 16 || tc / VEC > LF_BLOCK) return false;
+  const size_t cc4 = ((size_t)plan->ord.chunk_cols + 3) & ~(size_t)3;
   plan->tile_cols = tc;
-  plan->stages = stages;
-  plan->nt = nt;
-  plan->smem = (size_t)stages * tile_bytes + (size_t)3 * tc * sizeof(T) + (size_t)4 * npk * 16 + 128;
-  return plan->smem <= 100 * 1024;
+  plan->smem = ((size_t)LF_STAGES * tc * mb + 2 * cc4 + 2 * tc) * sizeof(T) + (size_t)4 * npk * 16 + 128;
+  return plan->smem <= smem_cap;
 }
 
 bool pb_bd_fista_eligible(const pb_ctx* ctx, int dtype, const pb_smooth* f, const pb_prox* g, const void* x, const void* z_prev, const void* grad,
@@ -323,24 +288,19 @@ bool pb_bd_fista_eligible(const pb_ctx* ctx, int dtype, const pb_smooth* f, cons
   return dtype == PB_F32 ? lf_plan<float>(ctx, f, g, x, z_prev, grad, z, x_next, &plan) : lf_plan<double>(ctx, f, g, x, z_prev, grad, z, x_next, &plan);
 }
 
-template <typename T, int PROX, int NT, int MINB>
-static int lf_launch_nt(pb_ctx* ctx, const LfParams& p, const LfPlan& plan) {
-  auto kern = k_bd_fista<T, PROX, NT, MINB>;
+template <typename T, int PROX>
+static int lf_launch(pb_ctx* ctx, const LfParams& p, const LfPlan& plan) {
+  auto kern = k_bd_fista<T, PROX>;
   static bool attr_done[PB_MAX_DEVICES] = {};
   const int dev = ctx->device < PB_MAX_DEVICES ? ctx->device : 0;
   if (!attr_done[dev] || ctx->device >= PB_MAX_DEVICES) {
-    PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done[dev] = true;
   }
   dim3 grid((unsigned)p.nchunk, (unsigned)p.nblk);
-  kern<<<grid, NT, plan.smem, ctx->stream>>>(p);
+  kern<<<grid, LF_BLOCK, plan.smem, ctx->stream>>>(p);
   PB_LAUNCH_CHECK(ctx);
   return PB_OK;
-}
-
-template <typename T, int PROX>
-static int lf_launch(pb_ctx* ctx, const LfParams& p, const LfPlan& plan) {
-  return plan.nt == 128 ? lf_launch_nt<T, PROX, 128, 5>(ctx, p, plan) : lf_launch_nt<T, PROX, 256, 2>(ctx, p, plan);
 }
 
 // One iteration: on entry f->r = A x - b; on return grad = A' r, z, x_next are written, f->r = A x_next - b and the scalar block holds
@@ -377,7 +337,6 @@ static int lf_run(pb_ctx* ctx, const pb_smooth* f, const pb_prox* g, double gamm
   p.t_lpc = plan.ord.t_lpc;
   p.t_kp = plan.ord.t_kp;
   p.tile_cols = plan.tile_cols;
-  p.stages = plan.stages;
   p.prox_kind = g->kind;
   p.gamma = (double)(T)gamma;
   p.beta = (double)(T)beta;
