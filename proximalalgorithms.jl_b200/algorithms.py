@@ -346,6 +346,17 @@ class FastForwardBackwardIteration(ForwardBackwardIteration):
             return seq.next(st.gamma)
         return self.R(next(seq))
 
+    def _next_beta_lookahead(self, st):
+        """The fixed-stepsize path fuses the NEXT iteration's extrapolation into the current pass, so it draws beta one iteration
+        before the reference does (fast_forward_backward.jl:134).  A finite user sequence may therefore run out here although the
+        driver would have stopped first: remember it and fail only if that next iteration is really taken (the value is irrelevant
+        until then: the speculative x_next is discarded)."""
+        try:
+            return self._next_beta(st)
+        except StopIteration:
+            st._sequence_exhausted = True
+            return self.R(0)
+
     def init(self):
         st = FastForwardBackwardState()
         e, fx = self._init_state(st)                                                        # :74-78
@@ -361,7 +372,7 @@ class FastForwardBackwardIteration(ForwardBackwardIteration):
         if not self.adaptive:
             # fixed stepsize: beta of the next step is a pure host scalar -> fuse its extrapolation into this pass
             st._x_next = t.empty_like(st.x)
-            st._beta_next = self._next_beta(st)
+            st._beta_next = self._next_beta_lookahead(st)
             g_of = e.fb_step(self.R, self.g, st.x, st.grad_f_x, st.gamma, st.z, z_prev=st.z_prev, beta=st._beta_next,
                              x_next=st._x_next, y_scratch=st._y_scratch)                    # :79-80, :89 (+ :135 of step 2)
         else:
@@ -382,12 +393,14 @@ class FastForwardBackwardIteration(ForwardBackwardIteration):
             fx = e.pre_resolve(R, self.g, e.eval_f(self.f, st.x, st.grad_f_x))              # :138-139
             g_of = e.fb_step(R, self.g, st.x, st.grad_f_x, st.gamma, st.z, y_scratch=st._y_scratch)    # :140-142
         else:
+            if getattr(st, "_sequence_exhausted", False):
+                raise RuntimeError("extrapolation_sequence is exhausted (fast_forward_backward.jl:99-104 draws one coefficient per iteration)")
             st.gamma = R(self.gamma)                                                        # :130-132
             st.beta = st._beta_next
             st.x, st._x_next = st._x_next, st.x                                             # :135 (computed by the previous pass)
             st.z_prev, st.z = st.z, st.z_prev                                               # :136
             fx = e.pre_resolve(R, self.g, e.eval_f(self.f, st.x, st.grad_f_x))              # :138-139
-            st._beta_next = self._next_beta(st)
+            st._beta_next = self._next_beta_lookahead(st)
             g_of = e.fb_step(R, self.g, st.x, st.grad_f_x, st.gamma, st.z, z_prev=st.z_prev, beta=st._beta_next,
                              x_next=st._x_next, y_scratch=st._y_scratch)                    # :140-142 (+ next :135)
         self._finish(st, fx, g_of)
@@ -448,7 +461,10 @@ class IterativeAlgorithm:
                 if self.verbose:
                     self.display(k, it, state)
                 self.last_iteration, self.last_state = it, state
-                return _like_input(it.x0, self.solution(it, state)), k                      # :119
+                sol = _like_input(it.x0, self.solution(it, state))                          # :119
+                if hasattr(state, "release"):     # states that own resources outside torch's allocator (row-sharded TV engine)
+                    state.release()
+                return sol, k
             if self.verbose and k % self.freq == 0:                                         # :121
                 self.display(k, it, state)
 
@@ -467,7 +483,11 @@ def _native_sequence(it, R):
     if isinstance(seq, SimpleNesterovSequence) and seq.R is R:
         return L.PB_SEQ_SIMPLE, 0.0
     if isinstance(seq, itertools.repeat):
-        return L.PB_SEQ_CONSTANT, float(R(next(seq)))
+        try:
+            seq.__length_hint__()              # repeat(x, times) is finite: only the Python loop reproduces its exhaustion
+            return None
+        except TypeError:                      # "len() of unsized object": the unbounded repeat(x)
+            return L.PB_SEQ_CONSTANT, float(R(next(seq)))
     return None
 
 

@@ -35,6 +35,19 @@ class DouglasRachfordState:
         self._mat = None          # (y, r, z, res) buffers of the fused path, filled on demand
         self._mat_valid = False
 
+    def release(self):
+        """Called by the solver driver once the solution has been copied out: a row-sharded TV run owns pb_malloc'ed ping-pong buffers
+        and cudaIpc mappings of its neighbours (outside torch's allocator).  `state.x` is a view of those buffers, so it is copied
+        first; y / z were materialised into ordinary tensors.  Collective in the sense that every rank does it after its last step."""
+        eng = getattr(self, "_tv", None)
+        if eng is not None and getattr(eng, "bufs", None):
+            self._materialise()                  # y, z of the final state (needs the buffers and the halo mappings)
+            self.x = self.x.clone()
+            if eng.sharded:
+                torch().cuda.synchronize(self.x.device)
+                self._it.f.comm.dist.barrier(group=getattr(self._it.f.comm, "group", None))   # nobody reads my rows any more
+            eng.close()
+
     def _materialise(self):
         if self._tv is not None:
             return self._materialise_tv()

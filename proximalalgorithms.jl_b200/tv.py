@@ -159,6 +159,13 @@ class TVDouglasRachfordEngine:
         self._opened = []
         if self.sharded:
             self._connect()
+            # Safety net for callers that drive the iterator themselves and drop it: when the engine is garbage collected its IPC
+            # mappings and pb_malloc'ed buffers (outside torch's caching allocator: ~1.3 GB per rank at 8192^2) are released.  The
+            # solver driver does not wait for the collector: it calls `state.release()` (douglas_rachford.py) as soon as the
+            # solution has been copied out.
+            import weakref
+
+            self._finalizer = weakref.finalize(self, _release_tv_resources, self.ctx, self._opened, self.bufs)
 
     def _connect(self):
         f, comm = self.f, self.f.comm
@@ -198,16 +205,26 @@ class TVDouglasRachfordEngine:
         return self.X[dst]
 
     def close(self):
-        """Unmap the neighbours' buffers and free this rank's (sharded runs only; idempotent).  Explicit on purpose: `state.x` is
-        a tensor view of these buffers, so they must outlive every reference a caller may still hold."""
-        for p in getattr(self, "_opened", []):
-            self.ctx.lib.pb_ipc_close(self.ctx.h, p)
+        """Unmap the neighbours' buffers and free this rank's (sharded runs only; idempotent).  `state.x` is a tensor view of these
+        buffers: callers that still need it copy it first (`DouglasRachfordState.release` does)."""
+        fin = getattr(self, "_finalizer", None)
+        if fin is not None:
+            fin.detach()
+            self._finalizer = None
+        _release_tv_resources(self.ctx, getattr(self, "_opened", []), getattr(self, "bufs", None))
         self._opened = []
-        if getattr(self, "bufs", None):
-            torch().cuda.synchronize(self.ctx.device)
-            for b_ in self.bufs:
-                b_.free()
-            self.bufs = None
+        self.bufs = None
+
+
+def _release_tv_resources(ctx, opened, bufs):
+    for p in list(opened):
+        ctx.lib.pb_ipc_close(ctx.h, p)
+    del opened[:]
+    if bufs:
+        torch().cuda.synchronize(ctx.device)
+        for b_ in bufs:
+            b_.free()
+        del bufs[:]
 
 
 __all__ = ["TVSplit", "IndConsensus"]

@@ -391,3 +391,29 @@ def test_panoc_reference_problems_with_user_callbacks(emu, golden, T):
             x, it = pa.PANOC(tol=1e-4)(x0=np.zeros(n), f=QP(), g=pa.IndBox(-1.0, 1.0))
             z = np.minimum(1.0, np.maximum(-1.0, x - gamma * (Q @ x + qv)))
             assert np.max(np.abs(x - z)) / gamma <= 1e-4 and it < 1000
+
+
+def test_finite_extrapolation_sequence_is_only_missed_when_really_needed(emu, golden):
+    """The fixed-stepsize path draws beta one iteration ahead of the reference (it fuses the next extrapolation into the current pass).
+    A finite user sequence must not fail before the iteration that really needs the missing coefficient."""
+    import itertools
+
+    T = np.float64
+    A, b, lam, _ = _lasso_4x5(golden, T)
+    Lf = T(np.linalg.norm(A, 2) ** 2)
+    kw = dict(x0=np.zeros(5, T), f=pa.LeastSquares(A, b), g=pa.NormL1(lam), Lf=Lf)
+    # the reference draws one coefficient per step: iterations 2, 3, 4 of a maxit = 4 run need 3 of them
+    z, k = pa.FastForwardBackward(tol=-1.0, maxit=4, driver="python")(extrapolation_sequence=iter([0.1, 0.2, 0.3]), **kw)
+    zr, kr = pa.FastForwardBackward(tol=-1.0, maxit=4, driver="python")(extrapolation_sequence=itertools.chain([0.1, 0.2, 0.3], itertools.repeat(0.9)), **kw)
+    assert k == kr == 4 and np.array_equal(z, zr)
+    with pytest.raises(RuntimeError, match="exhausted"):
+        pa.FastForwardBackward(tol=-1.0, maxit=6, driver="python")(extrapolation_sequence=iter([0.1, 0.2, 0.3]), **kw)
+    # a bounded itertools.repeat is not mistaken for the constant sequence of the native driver
+    from proxb200.algorithms import _native_sequence
+
+    class _It:
+        extrapolation_sequence = itertools.repeat(0.5, 3)
+
+    assert _native_sequence(_It, T) is None
+    _It.extrapolation_sequence = itertools.repeat(0.5)
+    assert _native_sequence(_It, T) is not None
