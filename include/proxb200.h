@@ -53,8 +53,12 @@ enum {
   PB_PROX_BOX = 2,     /* IndBox(lo,hi): clamp, value 0  (test/problems/test_nonconvex_qp.jl:19,33)       */
   PB_PROX_SCALE = 3,   /* z = s*y with a caller-supplied factor: phase 2 of IndBallL2 (s = min(1, r/||y||)) */
   PB_PROX_L21 = 4,     /* NormL21(lambda, dim=1) on contiguous groups of `group` elements                  */
-  PB_PROX_SQRL2 = 5    /* Translate(SqrNormL2(lambda), -b): f = lambda/2*||x - b||^2, b = v0 or 0
+  PB_PROX_SQRL2 = 5,   /* Translate(SqrNormL2(lambda), -b): f = lambda/2*||x - b||^2, b = v0 or 0
                           (test/problems/test_lasso_small.jl:38); prox z = (y - b)/(1 + gamma*lambda) + b           */
+  PB_PROX_BALL = 6     /* IndBallL2(r), p0 = r: z = y if ||y|| <= r else y*r/||y||, value 0.  pb_fb_step / pb_ffb_step / pb_solve only, one
+                          GPU: the step enqueues a reduction pass (||x - gamma*grad||^2 -> AUX3 slot) and the fused kernel forms the scale
+                          factor r/||y|| from that slot ON THE DEVICE -- no host round trip between the two phases.  Row-sharded iterates
+                          need the norm combined across ranks first: use pb_forward + exchange + PB_PROX_SCALE (PB_EUNSUPPORTED here) */
 };
 
 typedef struct pb_prox {

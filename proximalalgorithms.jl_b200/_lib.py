@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libproxb200.so")
 
 PB_F32, PB_F64 = 0, 1
-PB_PROX_ZERO, PB_PROX_L1, PB_PROX_BOX, PB_PROX_SCALE, PB_PROX_L21, PB_PROX_SQRL2 = 0, 1, 2, 3, 4, 5
+PB_PROX_ZERO, PB_PROX_L1, PB_PROX_BOX, PB_PROX_SCALE, PB_PROX_L21, PB_PROX_SQRL2, PB_PROX_BALL = 0, 1, 2, 3, 4, 5, 6
 PB_OPT_CTAS_PER_SM, PB_OPT_STREAM_HINTS, PB_OPT_UNROLL, PB_OPT_STEP_IMPL, PB_OPT_FUSED_EXCHANGE, PB_OPT_PERSISTENT, PB_OPT_MULTI_ITER, PB_OPT_GEMV_SCALAR, PB_OPT_LSQ_FUSED, PB_OPT_LSQ_FISTA = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 PB_IPC_HANDLE_BYTES, PB_MAX_WORLD = 64, 8
 PB_S_GSUM, PB_S_RESSQ, PB_S_GDR, PB_S_RESINF, PB_S_AUX, PB_S_AUXINF, PB_S_AUX2, PB_S_AUX3, PB_NSCALARS = 0, 2, 4, 6, 8, 10, 12, 14, 16

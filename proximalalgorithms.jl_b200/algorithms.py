@@ -100,8 +100,17 @@ class _Engine:
             else:
                 L.check(lib.pb_fb_step(ctx.h, dt, n, ptr(x), ptr(grad), float(gamma), C.byref(d), None, ptr(z), ptr(res_out)))
             return lambda sc: g.value_from(R, sc.gsum)
+        if isinstance(g, IndBallL2) and self.comm.size == 1:
+            # one GPU: both phases are enqueued by the library (norm pass -> AUX3 slot, scale factor formed on the device)
+            d = g.ball_descriptor(R)
+            if extrap:
+                L.check(lib.pb_ffb_step(ctx.h, dt, n, ptr(x), ptr(grad), ptr(z_prev), float(gamma), float(beta), C.byref(d),
+                                        None, ptr(z), ptr(res_out), ptr(x_next)))
+            else:
+                L.check(lib.pb_fb_step(ctx.h, dt, n, ptr(x), ptr(grad), float(gamma), C.byref(d), None, ptr(z), ptr(res_out)))
+            return lambda sc_: R(0)
         if isinstance(g, IndBallL2):
-            # phase 1: y and ||y||^2 (combined over shards); phase 2: fused step with the scale factor
+            # row shards: phase 1: y and ||y||^2 (combined over shards); phase 2: fused step with the scale factor
             L.check(lib.pb_forward(ctx.h, dt, n, ptr(x), ptr(grad), float(gamma), ptr(y_scratch)))
             sc = self.comm.exchange(ctx)
             d = g.scale_descriptor(R, sc.aux)
@@ -123,7 +132,7 @@ class _Engine:
         """A Deferred f value lives in the AUX slot until the iteration's read-back.  The two-phase (IndBallL2) and user-prox
         forms of the step run `pb_forward` first, which reuses that slot for ||y||^2: fetch the value before they do.  Fused
         prox kinds never touch AUX, so for them this is a no-op (no extra synchronisation)."""
-        if getattr(g, "fused", False) or not isinstance(fx, Deferred):
+        if getattr(g, "fused", False) or not isinstance(fx, Deferred) or (isinstance(g, IndBallL2) and self.comm.size == 1):
             return fx
         row, sc = self.read()
         return _resolve(fx, R, row, sc)
@@ -501,11 +510,12 @@ def _native_solve(alg, it):
     if tol is None or alg.solution is not default_solution or alg.verbose:
         return None
     f, g, R = it.f, it.g, it.R
-    if not hasattr(f, "native_descriptor") or not getattr(g, "fused", False):
-        return None
-    if g.kind not in (L.PB_PROX_ZERO, L.PB_PROX_L1, L.PB_PROX_BOX, L.PB_PROX_L21):
-        return None
     comm = it.comm
+    ball = isinstance(g, IndBallL2) and (comm is None or comm.size == 1)         # one GPU: PB_PROX_BALL, both phases on the device
+    if not hasattr(f, "native_descriptor") or not (getattr(g, "fused", False) or ball):
+        return None
+    if not ball and g.kind not in (L.PB_PROX_ZERO, L.PB_PROX_L1, L.PB_PROX_BOX, L.PB_PROX_L21):
+        return None
     if comm is not None and not isinstance(comm, (LocalComm, DeviceExchangeComm)):
         return None
     fdesc = f.native_descriptor()
@@ -563,7 +573,7 @@ def _native_solve(alg, it):
                            float(it.minimum_gamma), float(it.reduce_gamma), float(it.increase_gamma),
                            spare_x.data_ptr() if pipelined else None, spare_z.data_ptr() if pipelined else None,
                            scratch.data_ptr() if pipelined else None)
-    gdesc = g.descriptor(R)
+    gdesc = g.ball_descriptor(R) if ball else g.descriptor(R)
     res = L.pb_solve_result()
     t1 = time.perf_counter()
     L.check(e.lib.pb_solve(e.ctx.h, pb_dtype(R), n, C.byref(fdesc), C.byref(gdesc), C.byref(opts), ptr(x), ptr(grad), ptr(z), ptr(z_prev),

@@ -525,8 +525,9 @@ extern "C" int pb_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, c
   PB_REQUIRE(o->algorithm != PB_ALG_FFB || (z_prev && (o->adaptive || x_next)), "FFB needs z_prev (and x_next when the stepsize is fixed)");
   PB_REQUIRE(o->algorithm != PB_ALG_FB || !o->adaptive || grad_z, "adaptive FB needs grad_z");
   PB_REQUIRE(o->gamma > 0 || o->adaptive, "a fixed stepsize needs gamma > 0");
-  PB_REQUIRE(g->kind == PB_PROX_ZERO || g->kind == PB_PROX_L1 || g->kind == PB_PROX_BOX || g->kind == PB_PROX_L21,
-             "pb_solve supports the single-pass prox kinds (Zero, NormL1, IndBox, NormL21)");
+  PB_REQUIRE(g->kind == PB_PROX_ZERO || g->kind == PB_PROX_L1 || g->kind == PB_PROX_BOX || g->kind == PB_PROX_L21 ||
+                 (g->kind == PB_PROX_BALL && ctx->xchg_world <= 1),
+             "pb_solve supports Zero, NormL1, IndBox, NormL21 and (on one GPU) IndBallL2");
   PB_REQUIRE(f->kind != PB_F_LSQ_DENSE || ctx->xchg_world <= 1, "dense least squares is single-GPU in pb_solve (column shards need a vector all-gather)");
   memset(out, 0, sizeof(*out));
   PbDeviceGuard dev_guard(ctx);

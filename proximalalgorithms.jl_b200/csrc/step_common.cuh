@@ -14,11 +14,20 @@ __device__ __forceinline__ T prox_elem(T y, T a, T b) {
     return add_rn(y, sel);
   } else if constexpr (PROX == PB_PROX_BOX) {
     return (y < a) ? a : ((y > b) ? b : y);
-  } else if constexpr (PROX == PB_PROX_SCALE) {
+  } else if constexpr (PROX == PB_PROX_SCALE || PROX == PB_PROX_BALL) {
     return (a > T(1)) ? y : mul_rn(a, y);
   } else {
     return y;
   }
+}
+
+// IndBallL2 on one GPU: scale factor r / ||y|| in the element type from the (hi, lo) pair the reduction pass left in the AUX3 slot --
+// the arithmetic of functions.py: IndBallL2.scale_factor (sqrt of the rounded double sum, cast, one division in R)
+template <typename T>
+__device__ __forceinline__ T ball_scale(const double* out, T r) {
+  const double ysq = __dadd_rn(__ldcg(out + PB_S_AUX3), __ldcg(out + PB_S_AUX3 + 1));
+  const T ny = (T)sqrt(ysq);
+  return r / ny;
 }
 
 struct StepParams {

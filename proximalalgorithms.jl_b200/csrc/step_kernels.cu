@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step(StepParams p) {
   T* __restrict__ ro = static_cast<T*>(p.res);
   T* __restrict__ xo = static_cast<T*>(p.x_next);
   const T gamma = (T)p.gamma, beta = (T)p.beta;
-  const T pa = (T)p.a, pb = (T)p.b;
+  const T pa = PROX == PB_PROX_BALL ? ball_scale<T>(p.out, (T)p.a) : (T)p.a, pb = (T)p.b;
   const int64_t n = p.n;
   const int64_t ntiles = n / TILE;
 
@@ -324,7 +324,8 @@ enum {
   OP_ADD_SCALAR,    // out = a + s0
   OP_SUB,           // out = a - b;                                    sum = out^2
   OP_NRM2SQ,        // (no out)                                        sum = a^2,  max = |a|
-  OP_DOT            // (no out)                                        sum = a*b
+  OP_DOT,           // (no out)                                        sum = a*b
+  OP_FORWARD_NRM    // (no out)                                        sum = (a - s0*b)^2   (phase 1 of IndBallL2 inside the step)
 };
 
 struct EwParams {
@@ -354,6 +355,10 @@ __device__ __forceinline__ T ew_elem(T a, T b, T c, T s0, T s1, bool hb, bool hc
   } else if constexpr (OP == OP_PROX_SCALE) {
     o = prox_elem<T, PB_PROX_SCALE>(a, s0, s1);
   } else if constexpr (OP == OP_FORWARD) {
+    o = sub_rn(a, mul_rn(s0, b));
+    pa = pb = (double)o;
+    have_prod = true;
+  } else if constexpr (OP == OP_FORWARD_NRM) {
     o = sub_rn(a, mul_rn(s0, b));
     pa = pb = (double)o;
     have_prod = true;
@@ -392,8 +397,8 @@ __device__ __forceinline__ T ew_elem(T a, T b, T c, T s0, T s1, bool hb, bool hc
 template <typename T, int OP, int VEC, int UNROLL>
 __global__ void __launch_bounds__(PB_BLOCK) k_ew(EwParams p) {
   constexpr bool COMP = sizeof(T) == 8;
-  constexpr bool USES_B = (OP == OP_FORWARD || OP == OP_EXTRAP || OP == OP_SUB || OP == OP_DOT);
-  constexpr bool HAS_OUT = !(OP == OP_NRM2SQ || OP == OP_DOT);
+  constexpr bool USES_B = (OP == OP_FORWARD || OP == OP_EXTRAP || OP == OP_SUB || OP == OP_DOT || OP == OP_FORWARD_NRM);
+  constexpr bool HAS_OUT = !(OP == OP_NRM2SQ || OP == OP_DOT || OP == OP_FORWARD_NRM);
   constexpr int64_t TILE = (int64_t)PB_BLOCK * VEC * UNROLL;
   const T* __restrict__ a = static_cast<const T*>(p.a);
   const T* __restrict__ b = static_cast<const T*>(p.b);
@@ -616,6 +621,7 @@ static int launch_step_deferred(pb_ctx* ctx, StepParams p, const pb_prox* g, boo
     case PB_PROX_L1: rc = launch_step_t<T, PB_PROX_L1, EXTRAP>(ctx, p, vec_ok); break;
     case PB_PROX_BOX: rc = launch_step_t<T, PB_PROX_BOX, EXTRAP>(ctx, p, vec_ok); break;
     case PB_PROX_SQRL2: rc = launch_step_t<T, PB_PROX_SQRL2, EXTRAP>(ctx, p, vec_ok); break;
+    case PB_PROX_BALL: rc = launch_step_t<T, PB_PROX_BALL, EXTRAP>(ctx, p, vec_ok); break;
     default: rc = launch_step_t<T, PB_PROX_SCALE, EXTRAP>(ctx, p, vec_ok); break;
   }
   if (rc != PB_OK) return rc;
@@ -649,6 +655,7 @@ static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool ve
       if ((p.lo_v && !pb_aligned16(p.lo_v)) || (p.hi_v && !pb_aligned16(p.hi_v))) vec_ok = false;
       break;
     case PB_PROX_SCALE:
+    case PB_PROX_BALL:             // p.a = r; the kernel forms r / ||y|| from the AUX3 slot (step_common launched the norm pass)
       p.a = g->p0;
       break;
     case PB_PROX_SQRL2: {           // den = 1 + gamma*lambda in the element type (two roundings, as pb_dr_step / pb_prox_apply)
@@ -697,10 +704,16 @@ static int launch_step_prox(pb_ctx* ctx, StepParams p, const pb_prox* g, bool ve
       return launch_step_t<T, PB_PROX_BOX, EXTRAP>(ctx, p, vec_ok);
     case PB_PROX_SQRL2:
       return launch_step_t<T, PB_PROX_SQRL2, EXTRAP>(ctx, p, vec_ok);
+    case PB_PROX_BALL:
+      return launch_step_t<T, PB_PROX_BALL, EXTRAP>(ctx, p, vec_ok);
     default:
       return launch_step_t<T, PB_PROX_SCALE, EXTRAP>(ctx, p, vec_ok);
   }
 }
+
+template <int OP>
+static int launch_ew(pb_ctx* ctx, int dtype, int64_t n, const void* a, const void* b, const void* c, void* out, double s0, double s1,
+                     int sum_slot, int max_slot);
 
 static int step_common(pb_ctx* ctx, int dtype, int64_t n, const void* x, const void* grad, const void* z_prev,
                        double gamma, double beta, const pb_prox* g, void* y, void* z, void* res, void* x_next,
@@ -712,6 +725,15 @@ static int step_common(pb_ctx* ctx, int dtype, int64_t n, const void* x, const v
   PB_REQUIRE(n == 0 || (x && grad && z), "null vector");
   PB_REQUIRE(!extrap || n == 0 || (z_prev && x_next), "null z_prev / x_next");
   PB_REQUIRE(!extrap || n == 0 || x_next != x, "x_next must not alias x");
+  if (g->kind == PB_PROX_BALL && n > 0) {
+    // IndBallL2, phase 1: ||x - gamma*grad||^2 -> AUX3 (no output vector; phase 2 recomputes y with the same two roundings)
+    if (ctx->xchg_world > 1) {
+      pb_set_error("PB_PROX_BALL needs the norm of y combined across ranks: use pb_forward + exchange + PB_PROX_SCALE on row shards");
+      return PB_EUNSUPPORTED;
+    }
+    const int rc1 = launch_ew<OP_FORWARD_NRM>(ctx, dtype, n, x, grad, nullptr, nullptr, dtype == PB_F32 ? (double)(float)gamma : gamma, 0, PB_S_AUX3, -1);
+    if (rc1 != PB_OK) return rc1;
+  }
   StepParams p;
   p.x = x;
   p.grad = grad;

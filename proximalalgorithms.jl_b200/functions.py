@@ -493,6 +493,10 @@ class IndBallL2:
     def scale_descriptor(self, R, ysq):
         return L.pb_prox(L.PB_PROX_SCALE, 0, float(self.scale_factor(R, ysq)), 0.0, None, None)
 
+    def ball_descriptor(self, R):
+        """One GPU: PB_PROX_BALL -- the step enqueues the norm pass itself and forms r/||y|| on the device (no host round trip)."""
+        return L.pb_prox(L.PB_PROX_BALL, 0, float(R(self.r)), 0.0, None, None)
+
     def prox_enqueue(self, ctx, z, y, gamma, comm=None):
         R = real_type(y.dtype)
         L.check(ctx.lib.pb_nrm2sq(ctx.h, pb_dtype(R), y.numel(), ptr(y)))

@@ -113,6 +113,11 @@ class EmuLib:
         if kind == L.PB_PROX_SCALE:
             s = T(g.p0)
             return y.copy() if s > 1 else (s * y).astype(T)
+        if kind == L.PB_PROX_BALL:          # one-GPU IndBallL2: scale factor from ||y||^2 (the library forms it on the device)
+            ny = T(math.sqrt(_fsum_prod(y, y)))
+            with np.errstate(divide="ignore"):
+                sc = T(T(g.p0) / ny)
+            return y.copy() if sc > 1 else (sc * y).astype(T)
         if kind == L.PB_PROX_L21:
             gl = T(T(gamma) * T(g.p0))
             yg = y.reshape(-1, g.group)

@@ -310,12 +310,49 @@ def test_native_driver_equals_python_host(T):
             zp, itp = mk(tol=tol, maxit=300, driver="python")(x0=np.zeros(5000, T), f=f, g=pa.NormL1(T(0.3)), **kw)
             zn, itn = mk(tol=tol, maxit=300, driver="native")(x0=np.zeros(5000, T), f=f, g=pa.NormL1(T(0.3)), **kw)
             assert itn == itp and np.array_equal(zn, zp, equal_nan=True) and np.all(np.isfinite(zn))
-    # what the native driver cannot run falls back (auto) or refuses (native)
+    # IndBallL2 on one GPU runs natively too (PB_PROX_BALL: norm pass + scale factor formed on the device, no host round trip between
+    # the two phases) -- and the Python loop uses the same form: identical results
+    for mk, kw in ((pa.FastForwardBackward, dict(Lf=Lf)), (pa.FastForwardBackward, {}), (pa.ForwardBackward, {}), (pa.ForwardBackward, dict(Lf=Lf))):
+        sp, sn = mk(tol=tol, maxit=300, driver="python"), mk(tol=tol, maxit=300)
+        zp, itp = sp(x0=x0, f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)), **kw)
+        zn, itn = sn(x0=x0, f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)), **kw)
+        assert sn.last_driver == "native" and itn == itp and np.array_equal(zn, zp, equal_nan=True)
+        assert np.linalg.norm(zn.astype(np.float64)) <= 0.5 * (1 + 1e-5)
+    # ... and equals the two-phase form with the scale factor computed on the host (what row shards use): pb_forward + PB_PROX_SCALE
+    import ctypes as C
+
+    from proxb200 import _lib as L
+    from proxb200.host import Context, ptr
+
+    ctx = Context.get()
+    rng_ = np.random.default_rng(3)
+    nv = 100_003
+    xv, gv = (torch.as_tensor(rng_.standard_normal(nv).astype(T)).cuda() for _ in range(2))
+    dt_ = L.PB_F32 if T == np.float32 else L.PB_F64
+    for radius in (0.5, 1e6):
+        ball = pa.IndBallL2(T(radius))
+        z1, z2, ysc = torch.empty_like(xv), torch.empty_like(xv), torch.empty_like(xv)
+        d1 = ball.ball_descriptor(T)
+        L.check(ctx.lib.pb_fb_step(ctx.h, dt_, nv, ptr(xv), ptr(gv), 0.3, C.byref(d1), None, ptr(z1), None))
+        row1 = ctx.read_scalars()
+        L.check(ctx.lib.pb_forward(ctx.h, dt_, nv, ptr(xv), ptr(gv), 0.3, ptr(ysc)))
+        ysq = ctx.read_scalars()
+        d2 = ball.scale_descriptor(T, ysq[L.PB_S_AUX] + ysq[L.PB_S_AUX + 1])
+        L.check(ctx.lib.pb_fb_step(ctx.h, dt_, nv, ptr(xv), ptr(gv), 0.3, C.byref(d2), None, ptr(z2), None))
+        row2 = ctx.read_scalars()
+        assert torch.equal(z1, z2) and row1[L.PB_S_RESSQ] == row2[L.PB_S_RESSQ] and row1[L.PB_S_RESINF] == row2[L.PB_S_RESINF]
+    # what the native driver cannot run falls back (auto) or refuses (native): a user-defined proximable term
+    class MyBall:
+        def prox_(self, z, y, gamma):
+            nrm = float(torch.linalg.vector_norm(y))
+            z.copy_(y if nrm <= 0.5 else y * (0.5 / nrm))
+            return 0.0
+
     auto = pa.FastForwardBackward(tol=tol, maxit=50)
-    auto(x0=x0, f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)), Lf=Lf)
+    auto(x0=x0, f=pa.LeastSquares(A, b), g=MyBall(), Lf=Lf)
     assert auto.last_driver == "python"
     with pytest.raises(pa.ProxB200Error):
-        pa.FastForwardBackward(tol=tol, driver="native")(x0=x0, f=pa.LeastSquares(A, b), g=pa.IndBallL2(T(0.5)), Lf=Lf)
+        pa.FastForwardBackward(tol=tol, driver="native")(x0=x0, f=pa.LeastSquares(A, b), g=MyBall(), Lf=Lf)
 
 
 @pytest.mark.parametrize("T", TYPES)
