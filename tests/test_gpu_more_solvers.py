@@ -1,17 +1,12 @@
-"""GPU tests written AFTER this round's GPU budget was spent, i.e. never yet run on hardware.  They are opt-in until they have had a
-first run (`PROXB200_FIRST_RUN=1 python -m pytest tests/test_gpu_zz_first_run.py -m gpu`; planned for the start of the next round,
-DESIGN.md section 8) so that an unverified test cannot turn the verified suite red, and they sort last so that under `pytest -x` they
-could never mask it either.  Each has a CPU twin that exercises the same host logic against the oracle through the ABI emulation
-(tests/test_host_emulated.py: test_two_phase_and_user_prox_keep_the_smooth_value, test_afba_linear_program_host_logic)."""
+"""GPU tests of the two-phase / user-prox value hand-over (`_Engine.pre_resolve`), AFBA / VuCondat on the reference's linear program and the
+native PANOC driver.  Written at the end of round 1 without a hardware run (then opt-in); they ran green on B200 at the start of round 2
+and are part of the normal suite since.  CPU twins: tests/test_host_emulated.py."""
 import os
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-
-if os.environ.get("PROXB200_FIRST_RUN") != "1":
-    pytest.skip("first hardware run pending: set PROXB200_FIRST_RUN=1 to include these tests", allow_module_level=True)
 
 torch = pytest.importorskip("torch")
 if not torch.cuda.is_available():
