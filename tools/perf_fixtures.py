@@ -35,8 +35,18 @@ def main():
 
         pa = pa_
     res = {}
-    for name in ("tiny", "small", "medium"):
-        d = np.load(os.path.join(ROOT, "tests", "golden", f"lasso_{name}.npz"))
+
+    def config0():
+        # BASELINE.json configs[0] as written: 200 x 500 dense fp64 Lasso (seed 1, 25 non-zeros, lambda = 0.1 ||A'b||_inf)
+        rng = np.random.default_rng(1)
+        A_ = rng.standard_normal((200, 500))
+        xt = np.zeros(500)
+        xt[rng.choice(500, 25, replace=False)] = rng.standard_normal(25)
+        b_ = A_ @ xt + 0.01 * rng.standard_normal(200)
+        return dict(A=A_, b=b_, lam=0.1 * np.max(np.abs(A_.T @ b_)))
+
+    for name in ("tiny", "small", "medium", "config0_200x500"):
+        d = config0() if name.startswith("config0") else np.load(os.path.join(ROOT, "tests", "golden", f"lasso_{name}.npz"))
         A, b, lam = np.asfortranarray(d["A"]), d["b"], float(d["lam"])
         n = A.shape[1]
         x0 = np.zeros(n)
