@@ -40,7 +40,12 @@ class LBFGSOperator:
         self.n = x.numel()
         self.comm = comm or LocalComm()
         if self.comm.size != 1:
-            raise L.ProxB200Error("the device L-BFGS keeps its dot products on one GPU: sharded iterates are not supported yet")
+            from .host import DeviceExchangeComm
+
+            # row shards: every dot product of the two-loop chain is summed over the ranks INSIDE its kernel (NVLink exchange of the
+            # reducing CTA, csrc/qn_kernels.cu), which needs the device exchange attached to this context
+            if not (isinstance(self.comm, DeviceExchangeComm) and self.comm.ctx is self.ctx):
+                raise L.ProxB200Error("the device L-BFGS on row shards needs the device exchange (DeviceExchangeComm) of its context")
         h = C.c_void_p()
         L.check(self.ctx.lib.pb_lbfgs_create(self.ctx.h, pb_dtype(self.R), self.n, self.M, C.byref(h)))
         self.h = h

@@ -46,6 +46,7 @@ struct pb_ctx {
   int gemv_scalar;     // PB_OPT_GEMV_SCALAR: 1 = thread-per-row residual kernel (4-byte loads) instead of 16-byte row packs
   int multi_mode;      // PB_OPT_MULTI_ITER: 0 auto, -1 never, 1 force (even when contexts share a device)
   void* multi_ws;      // workspace of the persistent multi-iteration step kernel (step_multi.cu)
+  double* chain_dev;   // PB_NSCALARS doubles: rank-combined dots of a device-side chain (sharded L-BFGS recursion, qn_kernels.cu)
   double* scalars_dev;   // active scalar block (own or caller supplied)
   double* scalars_own;
   double* scalars_host;  // pinned mirror
@@ -273,10 +274,35 @@ __device__ __forceinline__ void fold_partials(Acc<NSUM, NMAX>& a, PbWorkspace* w
       if (map.max_slot[k] >= 0) out[map.max_slot[k]] = a.m[k];
     if (reset_ticket) ws->ticket = 0;  // ready for the next launch on this stream
   }
-  // fused C1: the CTA that produced the final scalars also exchanges them with the peers and hands them to the host
+  // fused C1: the CTA that produced the final scalars also exchanges them with the peers and hands them to the host -- or, for a
+  // device-side chain (gather_out), folds the ranks' rows itself so that the next kernel finds the global sums
   if (xp != nullptr && xp->world > 0) {
     __syncthreads();
-    xchg_push_wait(*xp, out);
+    if (xp->gather_out != nullptr) {
+      __shared__ double rows_sh[PB_MAX_RANKS * PB_NSCALARS];
+      const bool ok = xchg_push_gather(*xp, out, rows_sh);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NSUM; ++k)
+          if (map.sum_slot[k] >= 0) {
+            double hi = 0.0, lo = 0.0;
+            for (int r = 0; r < xp->world; ++r) {            // host-identical double-double fold in rank order (solve.cu: fold)
+              const double bh = rows_sh[r * PB_NSCALARS + map.sum_slot[k]], bl = rows_sh[r * PB_NSCALARS + map.sum_slot[k] + 1];
+              const double s = __dadd_rn(hi, bh);
+              const double bb = __dsub_rn(s, hi);
+              double e = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(bh, bb));
+              e = __dadd_rn(e, __dadd_rn(lo, bl));
+              const double h = __dadd_rn(s, e);
+              lo = __dsub_rn(e, __dsub_rn(h, s));
+              hi = h;
+            }
+            xp->gather_out[map.sum_slot[k]] = ok ? hi : __longlong_as_double(0x7ff8000000000000ll);
+            xp->gather_out[map.sum_slot[k] + 1] = lo;
+          }
+      }
+    } else {
+      xchg_push_wait(*xp, out);
+    }
   }
 }
 

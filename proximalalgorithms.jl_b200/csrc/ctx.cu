@@ -69,6 +69,7 @@ extern "C" int pb_ctx_create(int device, void* stream, int borrow_stream, pb_ctx
             cudaMallocHost(&c->scalars_host, PB_NSCALARS * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&c->ws, sizeof(PbWorkspace)) == cudaSuccess &&
             cudaMalloc(&c->multi_ws, pb_multi_ws_bytes()) == cudaSuccess &&
+            cudaMalloc((void**)&c->chain_dev, PB_NSCALARS * sizeof(double)) == cudaSuccess &&
             cudaMemsetAsync(c->scalars_own, 0, PB_NSCALARS * sizeof(double), c->stream) == cudaSuccess &&
             cudaMemsetAsync(c->ws, 0, sizeof(PbWorkspace), c->stream) == cudaSuccess &&
             cudaStreamSynchronize(c->stream) == cudaSuccess;
@@ -97,6 +98,7 @@ extern "C" int pb_ctx_destroy(pb_ctx* c) {
     if (c->hbuf[k]) cudaFree(c->hbuf[k]);
   if (c->scratch) cudaFree(c->scratch);
   if (c->multi_ws) cudaFree(c->multi_ws);
+  if (c->chain_dev) cudaFree(c->chain_dev);
   if (c->ws) cudaFree(c->ws);
   if (c->side_stream) {
     cudaStreamSynchronize(c->side_stream);

@@ -14,6 +14,7 @@
 //   * All kernels are single coalesced HBM passes with 16-byte packs; products are rounded separately from sums exactly
 //     like Julia's broadcasts (no FMA contraction); dots are exact for float data and double-double for double data.
 #include <new>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -318,6 +319,9 @@ struct QnParams {
   double* alpha_dev;
   PbWorkspace* ws;
   double* outs;
+  const double* dot_src;   // scalar block the coefficient's dot product is read from: `outs` on one GPU, the rank-combined copy
+                           // (pb_ctx::chain_dev) when the vectors are row shards
+  XchgParams xchg;         // world > 0: the dot this launch reduces is exchanged and folded over the ranks inside the kernel
 };
 
 template <typename T, int VEC>
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(PB_BLOCK) k_qn(QnParams p) {
   // coefficient from the dot product the previous launch left in the scalar block (kernel boundary = visibility)
   T c = T(0);
   if (p.mode != 2) {
-    const volatile double* o = p.outs;
+    const volatile double* o = p.dot_src;
     const T dotv = (T)(o[PB_S_AUX] + o[PB_S_AUX + 1]);          // real(dot(.,.)) rounded to R
     const T q = dotv / (T)p.ys;                                  // lbfgs.jl:77, :92
     if (p.mode == 0) {
@@ -382,11 +386,20 @@ __global__ void __launch_bounds__(PB_BLOCK) k_qn(QnParams p) {
     map.sum_slot[0] = PB_S_AUX;
     map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
     map.max_slot[0] = map.max_slot[1] = -1;
-    grid_reduce<1, 0, PB_BLOCK>(acc, p.ws, p.outs, map);
+    grid_reduce<1, 0, PB_BLOCK>(acc, p.ws, p.outs, map, &p.xchg);
   }
 }
 
-static int launch_qn(pb_ctx* ctx, int dtype, const QnParams& p) {
+static int launch_qn(pb_ctx* ctx, int dtype, QnParams p) {
+  // row shards (device exchange attached, world > 1): every dot of the chain is summed over the ranks inside the kernel
+  const bool sharded = ctx->xchg_world > 1 && ctx->xchg_connected;
+  memset(&p.xchg, 0, sizeof(p.xchg));
+  p.dot_src = sharded ? ctx->chain_dev : p.outs;
+  if (sharded && p.w) {
+    pb_xchg_next(ctx, &p.xchg, true);
+    p.xchg.gather_out = ctx->chain_dev;
+    ctx->xchg_pending = 0;              // nothing of this exchange reaches the host: a later read publishes the block afresh
+  }
   const bool vec_ok = pb_aligned16(p.d_in) && pb_aligned16(p.d_out) && (!p.u || pb_aligned16(p.u)) &&
                       (!p.w || pb_aligned16(p.w)) && (!p.x || (pb_aligned16(p.x) && pb_aligned16(p.xd)));
   if (dtype == PB_F32) {
@@ -442,7 +455,21 @@ extern "C" int pb_lbfgs_apply(pb_ctx* ctx, pb_lbfgs* L, const void* v, double sc
     if (idx == 0) idx = M;
   }
   // first dot: <s_{i1}, v>
-  int rc = pb_dot(ctx, L->dtype, L->n, lb_s(L, order[0]), v);
+  int rc;
+  if (ctx->xchg_world > 1 && ctx->xchg_connected) {
+    // row shards: the dot must be summed over the ranks on the device -> a copy link of the chain (d = v) carries it
+    p.d_in = v;
+    p.u = nullptr;
+    p.w = lb_s(L, order[0]);
+    p.d_out = d;
+    p.ys = 1.0;
+    p.post1 = p.post2 = 1.0;
+    p.mode = 2;
+    p.slot = 0;
+    rc = launch_qn(ctx, L->dtype, p);
+  } else {
+    rc = pb_dot(ctx, L->dtype, L->n, lb_s(L, order[0]), v);
+  }
   if (rc != PB_OK) return rc;
   for (int k = 0; k < m; ++k) {                       // loop 1
     const int sl = order[k];

@@ -32,6 +32,9 @@ struct XchgParams {
   unsigned long long* host_words;           // device alias of mapped pinned memory: [parity][PB_MAX_RANKS][32] words
   unsigned int seq;                         // sequence number of this exchange (never 0, never PB_XCHG_ERROR_SEQ)
   int rank, world;                          // world == 0: exchange disabled
+  double* gather_out;                       // non-NULL: the reducing CTA folds the ranks' rows itself (rank order, double-double) and
+                                            // leaves the GLOBAL sums here (scalar-block layout) instead of forwarding rows to the host:
+                                            // the next kernel of a device-side chain reads them (sharded L-BFGS two-loop recursion)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {

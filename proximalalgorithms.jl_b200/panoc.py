@@ -61,7 +61,7 @@ class PANOCIteration:
     """panoc.jl:41-53.  `A=None` is the identity; a numpy / torch matrix is wrapped into a device `MatrixOp`."""
 
     def __init__(self, x0, f=None, A=None, g=None, alpha=0.95, beta=0.5, Lf=None, gamma=None, adaptive=None,
-                 minimum_gamma=1e-7, max_backtracks=20, directions=None, comm=None):
+                 minimum_gamma=1e-7, max_backtracks=20, directions=None, comm=None, n_global=None):
         R = real_type(x0.dtype)
         self.R = R
         self.x0 = x0
@@ -79,6 +79,7 @@ class PANOCIteration:
         self.directions = directions if directions is not None else LBFGS(5)
         self.style = acceleration_style(self.directions)
         self.comm = comm
+        self.n_global = n_global     # length of the whole iterate when x0 is this rank's row shard
         self.backtracks = 0          # stepsize halvings (fb_tools.jl:46-55)
         self.tau_backtracks = 0      # line-search halvings (panoc.jl:203-250)
 
@@ -115,8 +116,8 @@ class PANOCIteration:
         R, t = self.R, torch()
         st = PANOCState()
         e = _Engine(self, self.x0)
-        if e.comm.size != 1:
-            raise L.ProxB200Error("PANOC runs on one GPU (the L-BFGS recursion needs un-sharded dot products)")
+        if e.comm.size != 1 and self.A is not None:
+            raise L.ProxB200Error("row-sharded PANOC supports A = I only (a matrix A would need its products combined across ranks)")
         st._engine, st._R = e, R
         dt = pb_dtype(R)
         ident = self.A is None
@@ -140,7 +141,8 @@ class PANOCIteration:
             if not ident:
                 L.check(e.lib.pb_nrm2sq(e.ctx.h, dt, n, ptr(self.A.mul_t_into(xeps, geps))))
             _, sc2 = e.read()
-            lower = R(R(np.sqrt(np.float64(sc2.aux))) / R(np.sqrt(np.float64(n))))
+            n_glob = self.n_global if self.n_global is not None else n * e.comm.size
+            lower = R(R(np.sqrt(np.float64(sc2.aux))) / R(np.sqrt(np.float64(n_glob))))
             with np.errstate(divide="ignore"):
                 st.gamma = R(self.alpha / lower)
         else:
@@ -151,7 +153,7 @@ class PANOCIteration:
         fx = e.pre_resolve(R, self.g, fx)
         g_of = self._step_kernel(st)                                                        # :97-98, :109
         self._read(st, fx, g_of)
-        st.H = self.directions.initialize(st.x) if self.style is QuasiNewtonStyle else None   # :110
+        st.H = self.directions.initialize(st.x, comm=e.comm) if self.style is QuasiNewtonStyle else None   # :110
         st.tau = R(0)
         # work vectors (:69-82).  Pools: the "copies" of the reference are renames between these buffers.
         st.x_prev, st.x_d, st._x_spare = new_n(), new_n(), None

@@ -95,6 +95,13 @@ def _worker(rank, world, port, exchange, q):
             mk = pa_.ForwardBackward if name.startswith("fb") else pa_.FastForwardBackward
             z, it = mk(tol=1e-7, maxit=5000)(x0=x0, f=f, g=pa_.NormL1(lam), comm=comm, n_global=n, **kw)
             out[name] = (it, z)
+        if exchange == "device":
+            # row-sharded PANOC + L-BFGS(5): every dot of the two-loop recursion is summed over the ranks inside its kernel
+            for name, g_, kw in (("panoc_l1", pa_.NormL1(lam), {}), ("panoc_l21_fixed", pa_.NormL21(lam, 4), dict(Lf=Lf)),
+                                 ("panoc_l1_lbfgs2", pa_.NormL1(lam), dict(directions=pa_.LBFGS(2)))):
+                alg = pa_.PANOC(tol=1e-7, maxit=2000)
+                z, it = alg(x0=x0, f=f, g=g_, comm=comm, n_global=n, **kw)
+                out[name] = (it, z, alg.last_iteration.tau_backtracks, alg.last_iteration.backtracks)
         q.put((rank, out))
         dist.barrier()
     finally:
@@ -135,3 +142,13 @@ def test_two_rank_sharded_solve_equals_single_gpu(exchange):
         mk_o = o.forward_backward if name.startswith("fb") else o.fast_forward_backward
         z_o, it_o = mk_o(np.zeros(nblk * nb), fo, o.NormL1(lam), tol=1e-7, maxit=5000, **kw)
         assert abs(it1 - it_o) <= max(2, it_o // 100) and np.max(np.abs(z1 - z_o)) <= 1e-8
+    if exchange == "device":
+        for name, g_, kw in (("panoc_l1", pa.NormL1(lam), {}), ("panoc_l21_fixed", pa.NormL21(lam, 4), dict(Lf=Lf)),
+                             ("panoc_l1_lbfgs2", pa.NormL1(lam), dict(directions=pa.LBFGS(2)))):
+            alg = pa.PANOC(tol=1e-7, maxit=2000, driver="python")
+            z1, it1 = alg(x0=np.zeros(nblk * nb), f=f, g=g_, **kw)
+            z2 = np.concatenate([res[r][name][1] for r in range(world)])
+            assert res[0][name][0] == res[1][name][0] == it1, (name, res[0][name][0], it1)
+            assert res[0][name][2:] == res[1][name][2:] == (alg.last_iteration.tau_backtracks, alg.last_iteration.backtracks)
+            assert np.array_equal(z2, z1), (name, float(np.max(np.abs(z2 - z1))))
+            assert 1 < it1 < 2000
