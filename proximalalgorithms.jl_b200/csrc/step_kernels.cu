@@ -153,12 +153,20 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step_l21(StepParams p, int group) 
       else
         ss.hi = __fma_rn((double)yv, (double)yv, ss.hi);
     }
+    if constexpr (COMP) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      dd o;
-      o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
-      o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
-      ss = dd_sum(ss, o);
+      for (int off = 16; off > 0; off >>= 1) {
+        dd o;
+        o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
+        o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
+        ss = dd_sum(ss, o);
+      }
+    } else {
+      // float data: the lane sums are sums of exact double products; a plain double shuffle tree keeps ~1e-16 relative accuracy on a
+      // value that is rounded to float right after (the double-double tree cost ~70 FP64 instructions per group and per lane: half of
+      // the FP64 pipe at HBM speed)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ss.hi = __dadd_rn(ss.hi, __shfl_xor_sync(0xffffffffu, ss.hi, off));
     }
     // nslice = sqrt(sum) in the element type; scal = 1 - gl/nslice, clamped at 0 (NaN propagates like the package)
     const T ns = (T)sqrt(ss.hi + ss.lo);
@@ -258,12 +266,20 @@ __global__ void __launch_bounds__(PB_BLOCK) k_step_l21_vec(StepParams p) {
         else
           ss.hi = __fma_rn((double)yv[q].v[e], (double)yv[q].v[e], ss.hi);
       }
+    if constexpr (COMP) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      dd o;
-      o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
-      o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
-      ss = dd_sum(ss, o);
+      for (int off = 16; off > 0; off >>= 1) {
+        dd o;
+        o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
+        o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
+        ss = dd_sum(ss, o);
+      }
+    } else {
+      // float data: the lane sums are sums of exact double products; a plain double shuffle tree keeps ~1e-16 relative accuracy on a
+      // value that is rounded to float right after (the double-double tree cost ~70 FP64 instructions per group and per lane: half of
+      // the FP64 pipe at HBM speed)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ss.hi = __dadd_rn(ss.hi, __shfl_xor_sync(0xffffffffu, ss.hi, off));
     }
     const T ns = (T)sqrt(ss.hi + ss.lo);
     T scal = sub_rn(T(1), gl / ns);
@@ -498,12 +514,20 @@ __global__ void __launch_bounds__(PB_BLOCK) k_prox_l21(const T* __restrict__ y, 
       else
         ss.hi = __fma_rn(yv, yv, ss.hi);
     }
+    if constexpr (COMP) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      dd o;
-      o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
-      o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
-      ss = dd_sum(ss, o);
+      for (int off = 16; off > 0; off >>= 1) {
+        dd o;
+        o.hi = __shfl_xor_sync(0xffffffffu, ss.hi, off);
+        o.lo = __shfl_xor_sync(0xffffffffu, ss.lo, off);
+        ss = dd_sum(ss, o);
+      }
+    } else {
+      // float data: the lane sums are sums of exact double products; a plain double shuffle tree keeps ~1e-16 relative accuracy on a
+      // value that is rounded to float right after (the double-double tree cost ~70 FP64 instructions per group and per lane: half of
+      // the FP64 pipe at HBM speed)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ss.hi = __dadd_rn(ss.hi, __shfl_xor_sync(0xffffffffu, ss.hi, off));
     }
     const T ns = (T)sqrt(ss.hi + ss.lo);
     T scal = sub_rn(T(1), gl / ns);

@@ -45,6 +45,25 @@ def main():
         res.append(dict(kind="dense", m=m, n=n, dtype=str(dt), ms_value_and_gradient=ms_f, gbs_both=2 * byt / ms_f / 1e6))
         print(res[-1], flush=True)
         del A, f
+    # The tensor-core question: would the 2-right-hand-side form A*[z x] (SURVEY.md section 7.8 ii) on the tensor pipe beat the
+    # streaming GEMV?  Library GEMM (cuBLAS through torch, TF32 tensor cores allowed) on the same 4 GB matrix with 1, 2 and 8 right-hand sides,
+    # against our single-RHS product: all of them are bound by reading A once from HBM (off the parity path: different arithmetic).
+    m, n = 10_000, 100_000
+    A = torch.randn(m, n, device="cuda")
+    torch.backends.cuda.matmul.allow_tf32 = True
+    for k in (1, 2, 8):
+        X = torch.randn(n, k, device="cuda")
+        ms = timeit(lambda: torch.mm(A, X), reps=20)
+        res.append(dict(kind="cublas_tf32_gemm_A_times_k_rhs", m=m, n=n, k=k, ms=ms, gbs_of_A=A.numel() * 4 / ms / 1e6))
+        print(res[-1], flush=True)
+    b = torch.randn(m, device="cuda")
+    x = torch.randn(n, device="cuda")
+    f = pa.LeastSquares(A, b)
+    ms = timeit(lambda: f.value_into(ctx, x), reps=20)
+    res.append(dict(kind="ours_residual_single_rhs", m=m, n=n, ms=ms, gbs_of_A=A.numel() * 4 / ms / 1e6))
+    print(res[-1], flush=True)
+    del A, f
+    torch.cuda.empty_cache()
     # whole solves on the reference fixtures (adaptive, tol 1e-6) -> iterations/s
     for name in ("tiny", "small", "medium"):
         d = np.load(os.path.join(ROOT, "tests", "golden", f"lasso_{name}.npz"))
