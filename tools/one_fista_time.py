@@ -27,4 +27,5 @@ t0 = time.perf_counter()
 z, it = s(x0=x0, f=f, g=pa.NormL1(0.5), Lf=1100.0)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-print(f"mode {mode} TC {os.environ.get('PROXB200_LF_TC', 'default')}: {it / dt:.1f} it/s  {1e3 * dt / it:.4f} ms/it")
+env = {k[10:]: v for k, v in os.environ.items() if k.startswith("PROXB200_LF_")}
+print(f"mode {mode} {env}: {it / dt:.1f} it/s  {1e3 * dt / it:.4f} ms/it", flush=True)
