@@ -210,6 +210,16 @@ int pb_lsq_dense_residual(pb_ctx* ctx, int dtype, int64_t m, int64_t n, const vo
                           const void* b, void* r);
 int pb_lsq_dense_gradient(pb_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, int64_t lda, const void* r,
                           void* grad);
+/* Column shard of a dense m x n_global matrix on a rank of the device exchange (pb_xchg_init / pb_xchg_connect[_local]); SURVEY.md
+ * section 8e "Dense-A gradient under this partition".  A: this rank's columns [col_offset, col_offset + n_local), x: its slice.
+ * ONE kernel combines the rank's chunk partials, pushes them to every peer over NVLink and folds ALL chunks in global chunk order:
+ * r = A x - b and AUX = ||r||^2 are replicated on every rank and bit-identical to the single-GPU pb_lsq_dense_residual on the whole
+ * matrix.  Shard boundaries must be multiples of pb_lsq_dense_chunk_cols(dtype, m, n_global) (the last shard takes the remainder; empty
+ * shards are allowed).  flags & 1: AUX is written on rank 0 only (0 elsewhere) -- for callers that sum AUX over the ranks.
+ * grad = A_p' r is then the local pb_lsq_dense_gradient.  Every rank must make the same sequence of sharded calls. */
+int pb_lsq_dense_residual_sharded(pb_ctx* ctx, int dtype, int64_t m, int64_t n_local, const void* A, int64_t lda, const void* x,
+                                  const void* b, void* r, int64_t n_global, int64_t col_offset, int flags);
+int64_t pb_lsq_dense_chunk_cols(int dtype, int64_t m, int64_t n);
 /* block-diagonal ("implicit A via batched GEMV", BASELINE.json configs[1]): nblk blocks, block k is a column-major
  * mb x nb matrix at A + k*mb*nb; x has nblk*nb entries, r/b have nblk*mb. */
 int pb_lsq_blockdiag_residual(pb_ctx* ctx, int dtype, int64_t nblk, int64_t mb, int64_t nb, const void* A,
@@ -308,7 +318,8 @@ typedef struct pb_smooth {
   int32_t kind;          /* PB_F_*                                                                              */
   int32_t pad;
   int64_t m, n, lda;     /* dense: A is m x n column-major                                                      */
-  int64_t nblk, mb, nb;  /* block-diagonal: nblk column-major mb x nb blocks                                     */
+  int64_t nblk, mb, nb;  /* block-diagonal: nblk column-major mb x nb blocks.  Dense COLUMN SHARD on a rank of the
+                          * device exchange (world > 1): n = local columns, nb = n_global, nblk = col_offset            */
   const void* A;         /* device matrix (dense / block-diagonal)                                              */
   const void* b;         /* device: right-hand side (least squares), b (SquaredDistance) or c (LinearFunction)   */
   void* r;               /* device scratch for the residual: m or nblk*mb entries                               */

@@ -114,6 +114,8 @@ SIGNATURES = {
     "pb_dot": (_i, [_vp, _i, _i64, _vp, _vp]),
     "pb_lsq_dense_residual": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _vp, _vp, _vp]),
     "pb_lsq_dense_gradient": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "pb_lsq_dense_residual_sharded": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i]),
+    "pb_lsq_dense_chunk_cols": (_i64, [_i, _i64, _i64]),
     "pb_lsq_blockdiag_residual": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "pb_lsq_blockdiag_gradient": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp]),
     "pb_lsq_blockdiag_value_and_gradient": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -37,7 +37,7 @@ from .tv import IndConsensus, TVSplit  # noqa: F401
 from .panoc import PANOC, PANOCIteration, PANOCState  # noqa: F401
 from . import iteration_tools as IterationTools  # noqa: F401
 from .jld2 import load_lasso_fixture, read_jld2  # noqa: F401
-from .host import Context, DeviceExchangeComm, LocalComm, Scalars, TorchDistComm, shard_bounds  # noqa: F401
+from .host import Context, DeviceExchangeComm, LocalComm, Scalars, TorchDistComm, dense_shard_bounds, shard_bounds  # noqa: F401
 from .nesterov import (  # noqa: F401
     AdaptiveNesterovSequence,
     ConstantNesterovSequence,

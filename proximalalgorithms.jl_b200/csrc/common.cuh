@@ -64,6 +64,7 @@ struct pb_ctx {
   unsigned long long* xchg_host_words;      // host pointer (pinned, mapped): [parity][PB_MAX_RANKS][32] words
   unsigned long long* xchg_host_words_dev;  // its device alias
   unsigned int xchg_seq;                    // last sequence number issued
+  unsigned int xchg_vseq;                   // last sequence number of the VECTOR exchange (C2, lsq_kernels.cu)
   int xchg_rank, xchg_world;                // world == 0: not initialised
   int xchg_connected;
   int xchg_local;                           // peers are contexts of this process (pb_xchg_connect_local): nothing to cudaIpcClose
@@ -84,6 +85,7 @@ struct pb_ctx {
 
 // Fill the kernel-side parameters for the next in-kernel exchange (advances the sequence number); world = 0 if disabled.
 void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want);
+void pb_xchg_vec_next(pb_ctx* ctx, XchgVecParams* xv);
 // Wait for one specific exchange (by sequence number) in the pinned landing zone; rows_out: world x PB_NSCALARS doubles.
 int pb_xchg_wait_seq(pb_ctx* ctx, unsigned int seq, double* rows_out, double timeout_s);
 int pb_step_defer(pb_ctx* ctx, int on);

@@ -211,6 +211,108 @@ __global__ void __launch_bounds__(PB_BLOCK) k_gemv_n_combine(const T* __restrict
   grid_reduce<1, 1, PB_BLOCK>(acc, ws, outs, map);
 }
 
+// C2 -- column-sharded dense A: combine + all-gather + fold in ONE kernel over NVLink peer memory (SURVEY.md section 8e "Dense-A
+// gradient under this partition").  Rank p holds the columns of the GLOBAL chunks [cbase, cbase + nloc) and has just computed their
+// partials.  Thread i (row i) 1. pushes its nloc partials to slot [parity][chunk][i] of EVERY peer's vector region (LL words
+// {32 data bits, 32-bit sequence}: xchg.cuh), 2. folds ALL nch chunks in GLOBAL chunk order -- its own from the local buffer, the
+// others from its landing zone as they arrive -- exactly like k_gemv_n_combine on one GPU, so r, ||r||^2 and everything downstream
+// are bit-identical for every shard count (and identical on every rank).  No thread waits before it has pushed: no co-residency
+// requirement, no deadlock.  aux_on == 0: this rank contributes 0 to AUX (the native driver sums AUX over the ranks).
+template <typename T>
+__global__ void __launch_bounds__(PB_BLOCK) k_gemv_n_combine_x(const T* __restrict__ partial, int nloc, int cbase, int nch, int64_t M,
+                                                               const T* __restrict__ b, T* __restrict__ r, PbWorkspace* ws, double* outs,
+                                                               XchgVecParams xv, int aux_on) {
+  constexpr bool COMP = sizeof(T) == 8;
+  constexpr int WPE = sizeof(T) / 4;          // 8-byte LL words per element
+  constexpr int BATCH = 8;
+  const int par = (int)(xv.seq & 1u);
+  const unsigned long long tag = (unsigned long long)xv.seq << 32;
+  unsigned long long* mine = xv.peer[xv.rank];
+  Acc<1, 1> acc;
+  acc.clear();
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * PB_BLOCK + threadIdx.x; i < M; i += (int64_t)gridDim.x * PB_BLOCK) {
+    // 1. push
+    for (int cl = 0; cl < nloc; ++cl) {
+      const T v = partial[(int64_t)cl * M + i];
+      unsigned int half[WPE];
+      if constexpr (COMP) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong((double)v);
+        half[0] = (unsigned int)(bits & 0xffffffffull);
+        half[WPE - 1] = (unsigned int)(bits >> 32);
+      } else {
+        half[0] = __float_as_uint((float)v);
+      }
+      const size_t slot = (((size_t)par * nch + (cbase + cl)) * (size_t)M + (size_t)i) * WPE;
+      for (int q = 0; q < xv.world; ++q) {
+        if (q == xv.rank) continue;
+#pragma unroll
+        for (int h = 0; h < WPE; ++h) st_word(xv.peer[q] + slot + h, tag | half[h]);
+      }
+    }
+    // 2. fold in global chunk order
+    T s = T(0);
+    for (int c0 = 0; c0 < nch; c0 += BATCH) {
+      unsigned long long w[BATCH][WPE];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int c = c0 + u;
+        if (c < nch && (c < cbase || c >= cbase + nloc)) {
+          const size_t slot = (((size_t)par * nch + c) * (size_t)M + (size_t)i) * WPE;
+#pragma unroll
+          for (int h = 0; h < WPE; ++h) w[u][h] = ld_word(mine + slot + h);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int c = c0 + u;
+        if (c >= nch) break;
+        T v;
+        if (c >= cbase && c < cbase + nloc) {
+          v = partial[(int64_t)(c - cbase) * M + i];
+        } else {
+          const size_t slot = (((size_t)par * nch + c) * (size_t)M + (size_t)i) * WPE;
+#pragma unroll
+          for (int h = 0; h < WPE; ++h) {
+            if (!bad && (unsigned int)(w[u][h] >> 32) != xv.seq) {      // (after one time-out the launch is lost: do not wait again)
+              const unsigned long long t0 = globaltimer_ns();
+              unsigned int spins = 0;
+              do {
+                w[u][h] = ld_word(mine + slot + h);
+                if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > PB_XCHG_TIMEOUT_NS) {
+                  bad = true;
+                  break;
+                }
+              } while ((unsigned int)(w[u][h] >> 32) != xv.seq);
+            }
+          }
+          if constexpr (COMP) {
+            const unsigned long long bits = (w[u][0] & 0xffffffffull) | ((w[u][WPE - 1] & 0xffffffffull) << 32);
+            v = (T)__longlong_as_double((long long)bits);
+          } else {
+            v = (T)__uint_as_float((unsigned int)(w[u][0] & 0xffffffffull));
+          }
+        }
+        s = c == 0 ? v : s + v;
+      }
+    }
+    T rv = b ? sub_rn(s, b[i]) : s;
+    if (bad) rv = (T)__longlong_as_double(0x7ff8000000000000ll);     // a peer never published: poison the result, flag the host
+    r[i] = rv;
+    if (COMP)
+      dd_add_prod(acc.s[0], (double)rv, (double)rv);
+    else
+      acc.s[0].hi = __fma_rn((double)rv, (double)rv, acc.s[0].hi);
+  }
+  if (bad) st_word(xv.err_word, (unsigned long long)PB_XCHG_ERROR_SEQ << 32);
+  if (!aux_on) acc.clear();
+  OutMap map;
+  map.sum_slot[0] = PB_S_AUX;
+  map.sum_slot[1] = map.sum_slot[2] = map.sum_slot[3] = -1;
+  map.max_slot[0] = map.max_slot[1] = -1;
+  grid_reduce<1, 1, PB_BLOCK>(acc, ws, outs, map);
+}
+
 // grad[k*nb + j] = sum_i A_k[i, j] * r[k*mb + i]   (warp per column)
 template <typename T>
 __global__ void __launch_bounds__(PB_BLOCK) k_gemv_t(const T* __restrict__ A, int64_t lda, int64_t blk_stride,
@@ -323,9 +425,15 @@ extern "C" int pb_sqdist(pb_ctx* ctx, int dtype, int64_t n, const void* x, const
   return pb_sub(ctx, dtype, n, x, b, grad);
 }
 
+// Column shard of a dense A (C2): the chunking is the one of the GLOBAL matrix and the fold runs over all ranks' chunks.
+struct LsqShard {
+  int64_t n_global, col_offset;
+  int aux_on;
+};
+
 template <typename T>
 static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T* A, int64_t lda, int64_t blk_stride,
-                      const T* x, const T* b, T* r) {
+                      const T* x, const T* b, T* r, const LsqShard* shard = nullptr) {
   const int64_t M = nblk * mb;
   if (M == 0) {
     // empty product: AUX = 0
@@ -336,15 +444,35 @@ static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
   // r_i is then the same on any GPU and for any sharding of the blocks over ranks, so a block-sharded run reproduces the
   // single-GPU bits.  ceil(nb/64) columns per chunk, clamped to [32, 4096]  ->  <= 64 chunks (more only for nb > 262144).
   // (the rule itself lives in lsq_order.h, shared with the persistent driver kernel)
-  const PbLsqOrder ord = pb_lsq_order(sizeof(T), nblk, mb, nb, lda, blk_stride, A, nullptr);
+  PbLsqOrder ord = pb_lsq_order(sizeof(T), nblk, mb, nb, lda, blk_stride, A, nullptr);
+  int64_t nch_global = 0, cbase = 0;
+  if (shard) {
+    // chunk columns of the GLOBAL matrix; this rank's columns must start on a chunk boundary and -- unless they are the last -- end on one
+    const PbLsqOrder og = pb_lsq_order(sizeof(T), 1, mb, shard->n_global, lda, 0, A, nullptr);
+    PB_REQUIRE((shard->col_offset % og.chunk_cols == 0 || (nb == 0 && shard->col_offset == shard->n_global)) &&
+                   (shard->col_offset + nb == shard->n_global || nb % og.chunk_cols == 0),
+               "column shards of a dense A must be aligned to the column chunks of the global matrix (pb_lsq_dense_chunk_cols)");
+    PB_REQUIRE(ord.n_sub == og.n_sub, "shard and global matrix disagree on the residual order");
+    ord.chunk_cols = og.chunk_cols;
+    ord.nchunk = (nb + og.chunk_cols - 1) / og.chunk_cols;          // 0 for an empty shard
+    nch_global = og.nchunk;
+    cbase = (shard->col_offset + og.chunk_cols - 1) / og.chunk_cols;      // (= nch_global for an empty shard behind the last column)
+    const size_t need = (size_t)2 * (size_t)nch_global * (size_t)M * (sizeof(T) / 4) * 8;
+    if (need > PB_XCHG_VEC_BYTES) {
+      pb_set_error("pb_lsq_dense_residual_sharded: %lld chunks x %lld rows exceed the vector exchange region", (long long)nch_global, (long long)M);
+      return PB_EUNSUPPORTED;
+    }
+  }
   const int64_t chunk_cols = ord.chunk_cols, nchunk = ord.nchunk;
-  PB_REQUIRE(nchunk <= 65535, "too many column chunks for one launch");
+  PB_REQUIRE(nchunk <= 65535 && nch_global <= 65535, "too many column chunks for one launch");
   (void)row_tiles;
   PB_REQUIRE(nblk <= 65535, "too many blocks for one launch (nblk <= 65535)");
-  int rc = pb_ensure_scratch(ctx, (size_t)nchunk * M * sizeof(T));
+  int rc = pb_ensure_scratch(ctx, (size_t)(nchunk > 0 ? nchunk : 1) * M * sizeof(T));
   if (rc != PB_OK) return rc;
   T* partial = static_cast<T*>(ctx->scratch);
-  if (ord.n_sub) {
+  if (nchunk == 0) {
+    // empty shard: nothing to compute, but this rank still takes part in the fold
+  } else if (ord.n_sub) {
     const int kp = ord.n_kp, lpc = ord.n_lpc;
 #define PB_LAUNCH_NSUB(L, KP_)                                                                                              \
   k_gemv_n_sub<T, L, KP_><<<(unsigned)(nblk * nchunk), PB_BLOCK, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk, \
@@ -379,9 +507,21 @@ static int residual_t(pb_ctx* ctx, int64_t nblk, int64_t mb, int64_t nb, const T
     k_gemv_n_partial<T><<<grid, GEMV_ROWS * GEMV_CL, 0, ctx->stream>>>(A, lda, blk_stride, x, partial, mb, nb, nblk,
                                                                       chunk_cols);
   }
-  PB_LAUNCH_CHECK(ctx);
-  const int cgrid = pb_stream_grid(ctx, PB_BLOCK, M, 2);
-  k_gemv_n_combine<T><<<cgrid, PB_BLOCK, 0, ctx->stream>>>(partial, (int)nchunk, M, b, r, ctx->ws, ctx->scalars_dev);
+  if (nchunk > 0) PB_LAUNCH_CHECK(ctx);
+  int cgrid = pb_stream_grid(ctx, PB_BLOCK, M, 2);
+  if (shard && ctx->xchg_shared_device) {
+    // peers on the same GPU: their (polling) kernels must fit beside this one
+    const int cap = (2 * ctx->sm_count) / (ctx->xchg_world > 0 ? ctx->xchg_world : 1);
+    if (cgrid > cap) cgrid = cap < 1 ? 1 : cap;
+  }
+  if (shard) {
+    XchgVecParams xv;
+    pb_xchg_vec_next(ctx, &xv);
+    k_gemv_n_combine_x<T><<<cgrid, PB_BLOCK, 0, ctx->stream>>>(partial, (int)nchunk, (int)cbase, (int)nch_global, M, b, r, ctx->ws,
+                                                               ctx->scalars_dev, xv, shard->aux_on);
+  } else {
+    k_gemv_n_combine<T><<<cgrid, PB_BLOCK, 0, ctx->stream>>>(partial, (int)nchunk, M, b, r, ctx->ws, ctx->scalars_dev);
+  }
   PB_LAUNCH_CHECK(ctx);
   return PB_OK;
 }
@@ -447,6 +587,35 @@ extern "C" int pb_lsq_dense_residual(pb_ctx* ctx, int dtype, int64_t m, int64_t 
   if (dtype == PB_F32)
     return residual_t<float>(ctx, 1, m, n, (const float*)A, lda, 0, (const float*)x, (const float*)b, (float*)r);
   return residual_t<double>(ctx, 1, m, n, (const double*)A, lda, 0, (const double*)x, (const double*)b, (double*)r);
+}
+
+// Column shard of a dense m x n_global matrix (this rank: columns [col_offset, col_offset + n_local), x its slice): r = A x - b,
+// replicated bit-identically on every rank and equal to the single-GPU r; AUX = ||r||^2 (flags & 1: on rank 0 only, 0 elsewhere).
+extern "C" int pb_lsq_dense_residual_sharded(pb_ctx* ctx, int dtype, int64_t m, int64_t n_local, const void* A, int64_t lda, const void* x,
+                                             const void* b, void* r, int64_t n_global, int64_t col_offset, int flags) {
+  int rc = check_common(ctx, dtype);
+  if (rc) return rc;
+  PB_REQUIRE(m >= 1 && n_local >= 0 && lda >= m, "bad shape (need m >= 1, n_local >= 0 and lda >= m)");
+  PB_REQUIRE(n_global >= 1 && col_offset >= 0 && col_offset + n_local <= n_global, "shard outside the matrix");
+  PB_REQUIRE(r != nullptr && (n_local == 0 || (A && x)), "null argument");
+  PB_REQUIRE(ctx->xchg_world >= 1 && ctx->xchg_connected, "device exchange not initialised / connected (pb_xchg_init, pb_xchg_connect)");
+  if (ctx->xchg_world == 1) {
+    PB_REQUIRE(n_local == n_global && col_offset == 0, "one rank holds the whole matrix");
+    return pb_lsq_dense_residual(ctx, dtype, m, n_local, A, lda, x, b, r);
+  }
+  LsqShard sh;
+  sh.n_global = n_global;
+  sh.col_offset = col_offset;
+  sh.aux_on = (flags & 1) ? (ctx->xchg_rank == 0) : 1;
+  if (dtype == PB_F32)
+    return residual_t<float>(ctx, 1, m, n_local, (const float*)A, lda, 0, (const float*)x, (const float*)b, (float*)r, &sh);
+  return residual_t<double>(ctx, 1, m, n_local, (const double*)A, lda, 0, (const double*)x, (const double*)b, (double*)r, &sh);
+}
+
+// Columns per chunk of the residual order for an m x n matrix: shard boundaries of a column-sharded dense A must be multiples of it.
+extern "C" int64_t pb_lsq_dense_chunk_cols(int dtype, int64_t m, int64_t n) {
+  const PbLsqOrder o = pb_lsq_order(dtype == PB_F32 ? 4 : 8, 1, m, n, m, 0, nullptr, nullptr);
+  return o.chunk_cols;
 }
 
 extern "C" int pb_lsq_dense_gradient(pb_ctx* ctx, int dtype, int64_t m, int64_t n, const void* A, int64_t lda,

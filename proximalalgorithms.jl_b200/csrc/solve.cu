@@ -138,7 +138,11 @@ struct Solver {
 
   int residual(const void* v) {     // f's residual pass at v; the value is Deferred in the AUX slot
     switch (f->kind) {
-      case PB_F_LSQ_DENSE: return pb_lsq_dense_residual(ctx, dtype, f->m, f->n, f->A, f->lda, v, f->b, f->r);
+      case PB_F_LSQ_DENSE:
+        // column shard (device exchange, world > 1): combine + NVLink all-gather + fold in one kernel; r and AUX replicated
+        if (ctx->xchg_world > 1)
+          return pb_lsq_dense_residual_sharded(ctx, dtype, f->m, f->n, f->A, f->lda, v, f->b, f->r, f->nb, f->nblk, 0);
+        return pb_lsq_dense_residual(ctx, dtype, f->m, f->n, f->A, f->lda, v, f->b, f->r);
       case PB_F_LSQ_BLOCKDIAG: return pb_lsq_blockdiag_residual(ctx, dtype, f->nblk, f->mb, f->nb, f->A, v, f->b, f->r);
       default: return PB_EUNSUPPORTED;
     }
@@ -528,7 +532,8 @@ extern "C" int pb_solve(pb_ctx* ctx, int dtype, int64_t n, const pb_smooth* f, c
   PB_REQUIRE(g->kind == PB_PROX_ZERO || g->kind == PB_PROX_L1 || g->kind == PB_PROX_BOX || g->kind == PB_PROX_L21 ||
                  (g->kind == PB_PROX_BALL && ctx->xchg_world <= 1),
              "pb_solve supports Zero, NormL1, IndBox, NormL21 and (on one GPU) IndBallL2");
-  PB_REQUIRE(f->kind != PB_F_LSQ_DENSE || ctx->xchg_world <= 1, "dense least squares is single-GPU in pb_solve (column shards need a vector all-gather)");
+  PB_REQUIRE(f->kind != PB_F_LSQ_DENSE || ctx->xchg_world <= 1 || (f->nb >= f->n && f->nblk >= 0 && f->nblk + f->n <= f->nb),
+             "a column-sharded dense least-squares term needs nb = n_global and nblk = col_offset (proxb200.h, pb_smooth)");
   memset(out, 0, sizeof(*out));
   PbDeviceGuard dev_guard(ctx);
   // cache-resident dense least squares: the whole loop runs on the device in one persistent kernel (persist.cu), same results

@@ -27,17 +27,31 @@ void pb_xchg_next(pb_ctx* ctx, XchgParams* xp, bool want) {
   xp->world = ctx->xchg_world;
 }
 
+// Parameters of the next vector exchange (C2).  The error word is the one behind the scalar landing zone.
+void pb_xchg_vec_next(pb_ctx* ctx, XchgVecParams* xv) {
+  memset(xv, 0, sizeof(*xv));
+  ctx->xchg_vseq += 1;
+  if (ctx->xchg_vseq == 0 || ctx->xchg_vseq == PB_XCHG_ERROR_SEQ) ctx->xchg_vseq = 1;
+  for (int r = 0; r < ctx->xchg_world; ++r)
+    xv->peer[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(ctx->xchg_peer[r]) + PB_XCHG_BYTES);
+  xv->err_word = ctx->xchg_host_words_dev + (size_t)2 * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW;
+  xv->seq = ctx->xchg_vseq;
+  xv->rank = ctx->xchg_rank;
+  xv->world = ctx->xchg_world;
+}
+
 extern "C" int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out) {
   PB_REQUIRE(ctx != nullptr, "null context");
   PB_REQUIRE(world >= 1 && world <= PB_MAX_RANKS && rank >= 0 && rank < world, "need 0 <= rank < world <= 8");
   PB_REQUIRE(ctx->xchg_world == 0, "exchange already initialised on this context");
   PB_CHECK_CUDA(cudaSetDevice(ctx->device));
   void* own = nullptr;
-  PB_CHECK_CUDA(cudaMalloc(&own, PB_XCHG_BYTES));
-  PB_CHECK_CUDA(cudaMemset(own, 0, PB_XCHG_BYTES));
+  const size_t own_bytes = PB_XCHG_BYTES + (world > 1 ? (size_t)PB_XCHG_VEC_BYTES : 0);   // scalar region + vector region (C2)
+  PB_CHECK_CUDA(cudaMalloc(&own, own_bytes));
+  PB_CHECK_CUDA(cudaMemset(own, 0, own_bytes));
   ctx->xchg_own = static_cast<unsigned long long*>(own);
   void* host = nullptr;
-  const size_t hbytes = (size_t)2 * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW * 8;   // [parity][rank][word]
+  const size_t hbytes = (size_t)2 * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW * 8 + 8;   // [parity][rank][word] + the vector-exchange error word
   PB_CHECK_CUDA(cudaHostAlloc(&host, hbytes, cudaHostAllocMapped | cudaHostAllocPortable));
   memset(host, 0, hbytes);
   ctx->xchg_host_words = static_cast<unsigned long long*>(host);
@@ -47,6 +61,7 @@ extern "C" int pb_xchg_init(pb_ctx* ctx, int rank, int world, void* handle_out) 
   ctx->xchg_rank = rank;
   ctx->xchg_world = world;
   ctx->xchg_seq = 0;
+  ctx->xchg_vseq = 0;
   ctx->xchg_pending = 0;
   ctx->xchg_connected = 0;
   for (int r = 0; r < PB_MAX_RANKS; ++r) ctx->xchg_peer[r] = nullptr;
@@ -170,6 +185,7 @@ extern "C" int pb_exchange_wait(pb_ctx* ctx, double* rows_out, double timeout_s)
 int pb_xchg_wait_seq(pb_ctx* ctx, unsigned int want, double* rows_out, double timeout_s) {
   const int nwords = ctx->xchg_world * PB_XCHG_WORDS_PER_ROW;
   volatile unsigned long long* words = ctx->xchg_host_words + (size_t)(want & 1u) * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW;
+  volatile unsigned long long* vec_err = ctx->xchg_host_words + (size_t)2 * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW;
   unsigned long long got[PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW];
   const double t0 = now_s();
   unsigned long long spins = 0;
@@ -193,6 +209,10 @@ int pb_xchg_wait_seq(pb_ctx* ctx, unsigned int want, double* rows_out, double ti
 #if defined(__x86_64__)
     __builtin_ia32_pause();
 #endif
+  }
+  if ((unsigned int)(*vec_err >> 32) == PB_XCHG_ERROR_SEQ) {
+    pb_set_error("pb_exchange_wait: a peer did not publish its chunk partials of A x within the device time-out (vector exchange)");
+    return PB_ECUDA;
   }
   for (int k = 0; k < ctx->xchg_world * PB_NSCALARS; ++k) {
     const unsigned long long bits = (got[2 * k] & 0xffffffffull) | ((got[2 * k + 1] & 0xffffffffull) << 32);

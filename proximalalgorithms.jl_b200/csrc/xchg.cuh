@@ -24,6 +24,9 @@
 #define PB_XCHG_WORDS_PER_ROW (2 * PB_NSCALARS)           // 32 eight-byte words per row
 #define PB_XCHG_WORDS (2 * PB_MAX_RANKS * PB_XCHG_WORDS_PER_ROW)   // [parity][rank][word]
 #define PB_XCHG_BYTES (PB_XCHG_WORDS * 8)
+// C2: behind the scalar region (same allocation, hence the same IPC handle) every rank owns a VECTOR region: the landing zone of the
+// chunk partials of r = A x for a column-sharded dense A (lsq_kernels.cu: k_gemv_n_combine_x).  [parity][global chunk][row][word]
+#define PB_XCHG_VEC_BYTES (128ull << 20)
 #define PB_XCHG_TIMEOUT_NS 4000000000ull                  // give up after 4 s (never hang the GPU)
 #define PB_XCHG_ERROR_SEQ 0xFFFFFFFFu
 
@@ -35,6 +38,13 @@ struct XchgParams {
   double* gather_out;                       // non-NULL: the reducing CTA folds the ranks' rows itself (rank order, double-double) and
                                             // leaves the GLOBAL sums here (scalar-block layout) instead of forwarding rows to the host:
                                             // the next kernel of a device-side chain reads them (sharded L-BFGS two-loop recursion)
+};
+
+struct XchgVecParams {
+  unsigned long long* peer[PB_MAX_RANKS];   // peer[r]: base of rank r's VECTOR region as mapped in this process
+  unsigned long long* err_word;             // device alias of a mapped pinned word: set to PB_XCHG_ERROR_SEQ << 32 on a time-out
+  unsigned int seq;                         // sequence number of this vector exchange (own counter; never 0 / PB_XCHG_ERROR_SEQ)
+  int rank, world;
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {

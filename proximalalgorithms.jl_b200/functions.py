@@ -141,17 +141,24 @@ class LeastSquares:
     `res = A*x - b; (norm(res)^2/2, A'*res)` (benchmark/benchmarks.jl:11-17).
 
     A is kept column-major on the device (Julia layout).  With `comm` of size P > 1, `A` is this rank's COLUMN shard
-    (matching the row shard of x): the m-vector of partial products is all-gathered and folded in rank order
-    (SURVEY.md section 8e), then `A_p' r` is local.
+    (matching the row shard of x) and `A_p' r` is local.  Two forms of the exchange:
+      * `comm` is a DeviceExchangeComm and `n_global`, `col_offset` are given (shards from `host.dense_shard_bounds`): ONE kernel
+        combines the rank's chunk partials, pushes them to the peers over NVLink and folds all chunks in global chunk order
+        (csrc/lsq_kernels.cu: k_gemv_n_combine_x) -- r, f and the whole solve are bit-identical to one GPU, and the native
+        driver loop (pb_solve) runs sharded;
+      * otherwise the m-vector of partial products is all-gathered with NCCL and folded in rank order (deterministic, every rank
+        the same, but not the single-GPU summation order).
     """
 
     is_generalized_quadratic = True      # ProximalOperators' trait of LeastSquares, read by panoc.jl:217
 
-    def __init__(self, A, b, comm=None, device=None):
+    def __init__(self, A, b, comm=None, device=None, n_global=None, col_offset=None):
         t = torch()
         ctx = Context.get(device)
         self.ctx = ctx
         self.comm = comm or LocalComm()
+        self.n_global, self.col_offset = n_global, col_offset
+        self.fused_gather = self.comm.size > 1 and n_global is not None and col_offset is not None and hasattr(self.comm, "timeout_s")
         if isinstance(A, t.Tensor):
             R = real_type(A.dtype)
             a_cm = A.to(ctx.device).t().contiguous()          # (n, m) row-major == A column-major
@@ -172,6 +179,10 @@ class LeastSquares:
         check_vec(x, self.n, self.A_cm.dtype)
         if self.comm.size == 1:
             L.check(lib.pb_lsq_dense_residual(ctx.h, dt, self.m, self.n, ptr(self.A_cm), self.m, ptr(x), ptr(self.b), ptr(self.r)))
+            return Deferred(lambda row, comb: _sq_half(self.R, row[L.PB_S_AUX] + row[L.PB_S_AUX + 1]))
+        if self.fused_gather:
+            L.check(lib.pb_lsq_dense_residual_sharded(ctx.h, dt, self.m, self.n, ptr(self.A_cm) if self.n else None, self.m, ptr(x) if self.n else None,
+                                                      ptr(self.b), ptr(self.r), int(self.n_global), int(self.col_offset), 0))
             return Deferred(lambda row, comb: _sq_half(self.R, row[L.PB_S_AUX] + row[L.PB_S_AUX + 1]))
         # column shard: partial product, all-gather, fixed-order fold, subtract b, ||r||^2 (replicated on every rank)
         L.check(lib.pb_lsq_dense_residual(ctx.h, dt, self.m, self.n, ptr(self.A_cm), self.m, ptr(x), None, ptr(self.r)))
@@ -220,9 +231,12 @@ class LeastSquares:
                 pass
 
     def native_descriptor(self):
-        """pb_smooth for the native driver (single GPU only: column shards need a vector all-gather per evaluation)."""
+        """pb_smooth for the native driver; a column shard qualifies when its exchange is the in-kernel one (fused_gather)."""
         if self.comm.size != 1:
-            return None
+            if not self.fused_gather:
+                return None
+            return L.pb_smooth(L.PB_F_LSQ_DENSE, 0, self.m, self.n, self.m, int(self.col_offset), 0, int(self.n_global),
+                               self.A_cm.data_ptr() if self.n else 0, self.b.data_ptr(), self.r.data_ptr())
         return L.pb_smooth(L.PB_F_LSQ_DENSE, 0, self.m, self.n, self.m, 0, 0, 0, self.A_cm.data_ptr(), self.b.data_ptr(), self.r.data_ptr())
 
     def value_and_gradient(self, x):

@@ -198,6 +198,21 @@ class DeviceExchangeComm:
             self.ctx = None
 
 
+def dense_shard_bounds(R, m: int, n: int, size: int):
+    """Column ranges [(lo, hi)] of a dense m x n matrix for `size` ranks of the device exchange: boundaries are multiples of the column
+    chunk of the residual order (csrc/lsq_order.h), which is what makes the sharded r = A x - b bit-identical to the single-GPU one
+    (include/proxb200.h: pb_lsq_dense_residual_sharded).  Ranks may come out empty when there are fewer chunks than ranks."""
+    cc = int(L.lib().pb_lsq_dense_chunk_cols(pb_dtype(R), m, n))
+    nch = (n + cc - 1) // cc
+    base, rem = divmod(nch, size)
+    out, c = [], 0
+    for r in range(size):
+        k = base + (1 if r < rem else 0)
+        out.append((min(n, c * cc), min(n, (c + k) * cc)))
+        c += k
+    return out
+
+
 def shard_bounds(n: int, size: int, align: int = 32):
     """Contiguous, `align`-element aligned index ranges of an n-vector over `size` ranks (last shard takes the remainder).
     align=32 keeps every fp32 shard 128-byte aligned; NormL21 callers pass a multiple of the group length."""

@@ -102,10 +102,32 @@ def _worker(rank, world, port, exchange, q):
                 alg = pa_.PANOC(tol=1e-7, maxit=2000)
                 z, it = alg(x0=x0, f=f, g=g_, comm=comm, n_global=n, **kw)
                 out[name] = (it, z, alg.last_iteration.tau_backtracks, alg.last_iteration.backtracks)
+        if exchange == "device":
+            # dense A, column-sharded: the chunk partials of A x are all-gathered inside the combine kernel (C2), native driver loop
+            from proxb200.host import dense_shard_bounds
+
+            Ad, bd, lamd, Lfd = _dense_problem()
+            lo, hi = dense_shard_bounds(np.float64, Ad.shape[0], Ad.shape[1], world)[rank]
+            fd = pa_.LeastSquares(Ad[:, lo:hi], bd, comm=comm, n_global=Ad.shape[1], col_offset=lo)
+            for name, kw in (("dense_ffb_adaptive", {}), ("dense_fb_adaptive", {}), ("dense_ffb_fixed", dict(Lf=Lfd))):
+                mk = pa_.ForwardBackward if "fb_" in name and "ffb" not in name else pa_.FastForwardBackward
+                alg = mk(tol=1e-7, maxit=3000)
+                z, it = alg(x0=np.zeros(hi - lo), f=fd, g=pa_.NormL1(lamd), comm=comm, n_global=Ad.shape[1], **kw)
+                out[name] = (it, z, alg.last_driver)
         q.put((rank, out))
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def _dense_problem():
+    rng = np.random.default_rng(21)
+    m, n = 150, 4000
+    A = np.asfortranarray(rng.standard_normal((m, n)) / np.sqrt(m))
+    xt = np.zeros(n)
+    xt[rng.choice(n, 30, replace=False)] = rng.standard_normal(30)
+    b = A @ xt + 0.01 * rng.standard_normal(m)
+    return A, b, 0.1 * np.max(np.abs(A.T @ b)), 1.05 * np.linalg.norm(A, 2) ** 2
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
@@ -143,6 +165,16 @@ def test_two_rank_sharded_solve_equals_single_gpu(exchange):
         z_o, it_o = mk_o(np.zeros(nblk * nb), fo, o.NormL1(lam), tol=1e-7, maxit=5000, **kw)
         assert abs(it1 - it_o) <= max(2, it_o // 100) and np.max(np.abs(z1 - z_o)) <= 1e-8
     if exchange == "device":
+        Ad, bd, lamd, Lfd = _dense_problem()
+        fd = pa.LeastSquares(Ad, bd)
+        for name, kw in (("dense_ffb_adaptive", {}), ("dense_fb_adaptive", {}), ("dense_ffb_fixed", dict(Lf=Lfd))):
+            mk = pa.ForwardBackward if "fb_" in name and "ffb" not in name else pa.FastForwardBackward
+            z1, it1 = mk(tol=1e-7, maxit=3000)(x0=np.zeros(Ad.shape[1]), f=fd, g=pa.NormL1(lamd), **kw)
+            z2 = np.concatenate([res[r][name][1] for r in range(world)])
+            assert res[0][name][0] == res[1][name][0] == it1, (name, res[0][name][0], it1)
+            assert res[0][name][2] == "native"
+            assert np.array_equal(z2, z1), (name, float(np.max(np.abs(z2 - z1))))
+            assert 3 < it1 < 3000
         for name, g_, kw in (("panoc_l1", pa.NormL1(lam), {}), ("panoc_l21_fixed", pa.NormL21(lam, 4), dict(Lf=Lf)),
                              ("panoc_l1_lbfgs2", pa.NormL1(lam), dict(directions=pa.LBFGS(2)))):
             alg = pa.PANOC(tol=1e-7, maxit=2000, driver="python")
