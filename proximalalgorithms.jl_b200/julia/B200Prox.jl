@@ -157,6 +157,46 @@ function value_and_gradient_into!(grad::B200Vector{T}, f::B200LeastSquares{T}, x
 end
 lsq_value(::Type{T}, s) where {T} = (nr = T(sqrt(pairsum(s, S_AUX))); nr^2 / 2)      # norm(res)^2/2, sqrt-then-square
 
+# ---- column shard of a dense A on a rank of a B200World (SURVEY.md section 8e): x is row-sharded, so A is column-sharded; the chunk
+# partials of A x are all-gathered and folded in global chunk order INSIDE the combine kernel (pb_lsq_dense_residual_sharded), which
+# makes r, f and the whole solve bit-identical to one GPU.  Shard boundaries: multiples of dense_chunk_cols(T, m, n).
+struct B200LeastSquaresShard{T}
+    ctx::B200Context
+    A::B200Vector{T}             # this rank's columns, column-major (m x n_local)
+    b::B200Vector{T}             # replicated
+    r::B200Vector{T}             # replicated on return
+    m::Int
+    n_local::Int
+    n_global::Int
+    col_offset::Int
+end
+dense_chunk_cols(::Type{T}, m, n) where {T} = Int(ccall((:pb_lsq_dense_chunk_cols, LIB), Int64, (Cint, Int64, Int64), pbdtype(T), m, n))
+function dense_shard_bounds(::Type{T}, m, n, P) where {T}       # 0-based half-open column ranges, one per rank
+    cc = dense_chunk_cols(T, m, n)
+    nch = cld(n, cc)
+    base, rem = divrem(nch, P)
+    out = Tuple{Int,Int}[]
+    c = 0
+    for r in 0:P-1
+        k = base + (r < rem ? 1 : 0)
+        push!(out, (min(n, c * cc), min(n, (c + k) * cc)))
+        c += k
+    end
+    return out
+end
+function B200LeastSquaresShard(ctx::B200Context, A::Matrix{T}, b::Vector{T}, lo::Int, hi::Int) where {T}
+    m, n = size(A)
+    return B200LeastSquaresShard{T}(ctx, B200Vector(ctx, vec(A[:, lo+1:hi])), B200Vector(ctx, b), B200Vector{T}(ctx, m), m, hi - lo, n, lo)
+end
+function value_and_gradient_into!(grad::B200Vector{T}, f::B200LeastSquaresShard{T}, x::B200Vector{T}) where {T}
+    check(ccall((:pb_lsq_dense_residual_sharded, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cint),
+                f.ctx.h, pbdtype(T), f.m, f.n_local, f.A.ptr, f.m, x.ptr, f.b.ptr, f.r.ptr, f.n_global, f.col_offset, 0))
+    check(ccall((:pb_lsq_dense_gradient, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                f.ctx.h, pbdtype(T), f.m, f.n_local, f.A.ptr, f.m, f.r.ptr, grad.ptr))
+    return nothing
+end
+
 function ProximalAlgorithms.value_and_gradient(f::B200LeastSquares{T}, x::B200Vector{T}) where {T}
     grad = similar(x)
     value_and_gradient_into!(grad, f, x)
@@ -396,6 +436,8 @@ mutable struct PbSolveResult  # mirrors `struct pb_solve_result`
 end
 
 smooth_descriptor(f::B200LeastSquares) = PbSmooth(PB_F_LSQ_DENSE, 0, f.m, f.n, f.m, 0, 0, 0, f.A.ptr, f.b.ptr, f.r.ptr)
+smooth_descriptor(f::B200LeastSquaresShard) =      # pb_smooth of a column shard: nblk = col_offset, nb = n_global (proxb200.h)
+    PbSmooth(PB_F_LSQ_DENSE, 0, f.m, f.n_local, f.m, f.col_offset, 0, f.n_global, f.A.ptr, f.b.ptr, f.r.ptr)
 
 "SquaredDistance (benchmark/benchmarks.jl:19-28) on a device vector: f(x) = norm(x - b)^2 / 2."
 struct B200SquaredDistance{T}
