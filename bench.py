@@ -421,11 +421,14 @@ def run_b200(args):
                                    else "k_step<float, L1, EXTRAP> (pb_ffb_step)",
                          "kernel_ms": kern_ms_max,
                          "algorithmic_bytes_per_launch": BYTES_PER_ELT * n, "peak_source": peak_src,
-                         "note": ("kernel_ms = CUDA-event duration of the K2 launches inside the timed region. --loop native with the device exchange "
-                                  "runs the pipelined driver (pb_solve look-ahead): K2 writes per-CTA partials and a 1-CTA kernel on a side stream "
-                                  "folds them and does the scalar exchange while the next K2 runs, so kernel_ms is the streaming pass alone; "
-                                  "--loop python / other exchanges: K2 includes the last-CTA fold (+ in-kernel exchange). kernel_only_* = the "
-                                  "un-split K2 back to back without exchange and read-back"),
+                         "note": (("kernel_ms = CUDA-event duration of the ONE persistent launch that runs all K iterations (k_step_multi: streaming "
+                                   "CTAs + a service CTA that folds the partials, exchanges the scalar block with the other GPUs inside the kernel and "
+                                   "takes the stop decision), divided by K: every iteration's fold, exchange and stop test are inside it. ")
+                                  if multi_iter else
+                                  ("kernel_ms = CUDA-event duration of the K2 launches inside the timed region (pipelined driver: K2 writes per-CTA "
+                                   "partials, a 1-CTA kernel on a side stream folds them and does the scalar exchange while the next K2 runs; "
+                                   "--loop python / other exchanges: K2 includes the last-CTA fold (+ in-kernel exchange)). ")) +
+                                 "kernel_only_* = the one-iteration K2 kernel (pb_ffb_step) launched back to back without exchange and read-back",
                          "kernel_only_ms": kern_only_ms, "kernel_only_achieved": BYTES_PER_ELT * n / (kern_only_ms * 1e-3) / 1e9,
                          "kernel_only_frac": BYTES_PER_ELT * n / (kern_only_ms * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
