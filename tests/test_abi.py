@@ -83,3 +83,24 @@ def test_missing_library_is_loud(tmp_path):
 
     with pytest.raises(_lib.ProxB200Error, match="no fallback"):
         _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_dense_shard_bounds_follow_the_chunk_rule(lib_built):
+    """Column shards of a dense A (C2) must start on the column chunks of the residual order (csrc/lsq_order.h: ceil(n/64) columns,
+    clamped to [32, 4096], rounded up to a multiple of 4); pure host code, no device needed."""
+    from proxb200 import _lib
+    from proxb200.host import dense_shard_bounds
+
+    lib = _lib.load(lib_built)
+    for n in (1, 31, 100, 3000, 100_000, 262_144, 1_000_003):
+        cc_ref = min(max((n + 63) // 64, 32), 4096)
+        cc_ref = (cc_ref + 3) & ~3
+        for dt in (_lib.PB_F32, _lib.PB_F64):
+            assert lib.pb_lsq_dense_chunk_cols(dt, 500, n) == cc_ref
+        for P in (1, 2, 3, 8):
+            b = dense_shard_bounds(np.float32, 500, n, P)
+            assert len(b) == P and b[0][0] == 0 and b[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(b, b[1:] + [(n, n)]):
+                assert lo <= hi == lo2 and (lo % cc_ref == 0 or lo == n) and (hi % cc_ref == 0 or hi == n)
+            sizes = [(hi - lo + cc_ref - 1) // cc_ref for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1                      # chunks dealt evenly
