@@ -540,8 +540,11 @@ def _native_solve(alg, it):
     # returned solution and `last_state` alias them.
     host_in = not (isinstance(it.x0, t.Tensor) and it.x0.is_cuda)
     pipelined = fast and not it.adaptive and isinstance(e.comm, DeviceExchangeComm) and getattr(alg, "pipeline", True)
+    # block-diagonal least squares with a fixed stepsize: the one-sweep kernel (csrc/lsq_fista.cu) is launched one iteration ahead of the
+    # stop decision whenever it has spare vectors, with or without the device exchange
+    lookahead = pipelined or (fast and not it.adaptive and getattr(alg, "pipeline", True) and fdesc.kind == L.PB_F_LSQ_BLOCKDIAG)
     n0 = int(np.prod(np.shape(it.x0))) if not isinstance(it.x0, t.Tensor) else it.x0.numel()
-    key = (n0, str(it.x0.dtype).replace("torch.", ""), e.ctx.index, fast, bool(it.adaptive), pipelined)
+    key = (n0, str(it.x0.dtype).replace("torch.", ""), e.ctx.index, fast, bool(it.adaptive), lookahead)
     cache = getattr(alg, "_workspace", None) if host_in else None
     if cache is not None and cache[0] == key:
         x, z, scratch, z_prev, x_next, grad_z, spare_x, spare_z, own_grad = cache[1]
@@ -558,8 +561,8 @@ def _native_solve(alg, it):
         # fixed-stepsize FFB through the device exchange: two spare vectors let pb_solve run ahead of the stop decision (one launch per
         # iteration: pb_solve_opts.spare_*; one persistent kernel: the third buffers of its x / z rings); `scratch` doubles as the
         # spare gradient buffer
-        spare_x = t.empty_like(x) if pipelined else None
-        spare_z = t.empty_like(x) if pipelined else None
+        spare_x = t.empty_like(x) if lookahead else None
+        spare_z = t.empty_like(x) if lookahead else None
         own_grad = None if hasattr(f, "gradient_buffer") else t.empty_like(x)
         if host_in:
             alg._workspace = (key, (x, z, scratch, z_prev, x_next, grad_z, spare_x, spare_z, own_grad))
@@ -571,8 +574,8 @@ def _native_solve(alg, it):
     opts = L.pb_solve_opts(L.PB_ALG_FFB if fast else L.PB_ALG_FB, 1 if it.adaptive else 0, seq[0], 1 if getattr(alg, "profile", False) else 0, alg.maxit, int(n_glob), float(tol),
                            0.0 if it.gamma is None else float(R(it.gamma)), float(getattr(it, "mf", 0.0)), seq[1],
                            float(it.minimum_gamma), float(it.reduce_gamma), float(it.increase_gamma),
-                           spare_x.data_ptr() if pipelined else None, spare_z.data_ptr() if pipelined else None,
-                           scratch.data_ptr() if pipelined else None)
+                           spare_x.data_ptr() if lookahead else None, spare_z.data_ptr() if lookahead else None,
+                           scratch.data_ptr() if lookahead else None)
     gdesc = g.ball_descriptor(R) if ball else g.descriptor(R)
     res = L.pb_solve_result()
     t1 = time.perf_counter()

@@ -50,6 +50,8 @@ struct pb_ctx {
   double* scalars_dev;   // active scalar block (own or caller supplied)
   double* scalars_own;
   double* scalars_host;  // pinned mirror
+  double* ahead_host;    // pinned, 2 x PB_NSCALARS: scalar blocks of two iterations in flight (look-ahead loops without the exchange)
+  cudaEvent_t ahead_ev[2];
   PbWorkspace* ws;
   int64_t launches;
   // scratch for the dense / block-diagonal products (partial sums of column chunks)

@@ -110,6 +110,11 @@ extern "C" int pb_ctx_destroy(pb_ctx* c) {
     cudaStreamDestroy(c->side_stream);
   }
   if (c->scalars_own) cudaFree(c->scalars_own);
+  if (c->ahead_host) {
+    cudaFreeHost(c->ahead_host);
+    cudaEventDestroy(c->ahead_ev[0]);
+    cudaEventDestroy(c->ahead_ev[1]);
+  }
   if (c->scalars_host) cudaFreeHost(c->scalars_host);
   if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -434,6 +434,11 @@ struct Solver {
     Comb c0;
     if ((rc = read_comb(ctx, &c0))) return rc;
     R f_cur = f_value(c0);
+    // one iteration of look-ahead when the caller gave spare vectors: without it the GPU idles for a host round trip after every sweep
+    const bool via_xchg = ctx->xchg_world > 0 && ctx->xchg_connected;
+    if (o->spare_x && o->spare_z && o->spare_grad && pb_aligned16(o->spare_x) && pb_aligned16(o->spare_z) && pb_aligned16(o->spare_grad) &&
+        (!via_xchg || ctx->xchg_fused))
+      return run_ffb_bd_fista_ahead(out, seq, f_cur, via_xchg);
     int64_t k = 1;
     for (;;) {
       const R beta = seq.next(gamma);
@@ -447,6 +452,91 @@ struct Solver {
       t = z_prev; z_prev = z; z = t;                            // :136
       ++k;
     }
+    return finish(out, k);
+  }
+
+  // The same loop with the sweep of iteration k+1 launched before the scalars of iteration k are examined (the discard rule of
+  // run_ffb_pipelined: iteration k+1 writes the third x / z buffer and the other gradient buffer, so the state of a stopping iteration k
+  // is intact; f->r is scratch).  The scalars of an iteration reach the host either through the exchange (sequence numbers, parity
+  // double-buffered landing zone) or, without one, through a 128-byte copy into one of two pinned slots followed by an event.
+  struct AheadMark {
+    unsigned int seq;
+    int slot;
+  };
+  int ahead_mark(bool via_xchg, int slot, AheadMark* m) {
+    m->slot = slot;
+    m->seq = ctx->xchg_seq;
+    if (via_xchg) return PB_OK;
+    PB_CHECK_CUDA(cudaMemcpyAsync(ctx->ahead_host + (size_t)slot * PB_NSCALARS, ctx->scalars_dev, PB_NSCALARS * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    PB_CHECK_CUDA(cudaEventRecord(ctx->ahead_ev[slot], ctx->stream));
+    return PB_OK;
+  }
+  int ahead_read(bool via_xchg, const AheadMark& m, Comb* c) {
+    if (via_xchg) return read_comb_seq(ctx, m.seq, c);
+    PB_CHECK_CUDA(cudaEventSynchronize(ctx->ahead_ev[m.slot]));
+    const double* rows = ctx->ahead_host + (size_t)m.slot * PB_NSCALARS;
+    c->gsum = fold(rows, 1, PB_S_GSUM);
+    c->res_sq = fold(rows, 1, PB_S_RESSQ);
+    c->gdr = fold(rows, 1, PB_S_GDR);
+    c->aux = fold(rows, 1, PB_S_AUX);
+    c->res_inf = fold_max(rows, 1, PB_S_RESINF);
+    c->local_aux = rows[PB_S_AUX] + rows[PB_S_AUX + 1];
+    return PB_OK;
+  }
+  int run_ffb_bd_fista_ahead(pb_solve_result* out, Nesterov<R>& seq, R f_cur, bool via_xchg) {
+    int rc;
+    if (!via_xchg && !ctx->ahead_host) {
+      void* h = nullptr;
+      PB_CHECK_CUDA(cudaMallocHost(&h, 2 * PB_NSCALARS * sizeof(double)));
+      PB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ahead_ev[0], cudaEventDisableTiming));
+      PB_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ahead_ev[1], cudaEventDisableTiming));
+      ctx->ahead_host = static_cast<double*>(h);
+    }
+    void* X[3] = {x, x_next, o->spare_x};
+    void* Z[3] = {z_prev, z, o->spare_z};
+    void* G[2] = {grad, o->spare_grad};
+    int ix = 0, ixn = 1, izp = 0, iz = 1, ig = 0;
+    AheadMark mk, mk_next;
+    mk_next.seq = 0;
+    mk_next.slot = 0;
+    {
+      const R beta = seq.next(gamma);
+      if ((rc = pb_bd_fista_step(ctx, dtype, f, g, (double)gamma, (double)beta, X[ix], Z[izp], G[ig], Z[iz], X[ixn]))) return rc;
+      if ((rc = ahead_mark(via_xchg, 1, &mk))) return rc;
+    }
+    int64_t k = 1;
+    for (;;) {
+      const bool spec = k < o->maxit;
+      const Nesterov<R> seq_saved = seq;
+      const int ixf = 3 - ix - ixn, izf = 3 - izp - iz, igo = 1 - ig;
+      if (spec) {                                       // fast_forward_backward.jl:130-142 for iteration k+1, launched ahead
+        const R beta = seq.next(gamma);
+        if ((rc = pb_bd_fista_step(ctx, dtype, f, g, (double)gamma, (double)beta, X[ixn], Z[iz], G[igo], Z[izf], X[ixf]))) return rc;
+        if ((rc = ahead_mark(via_xchg, (int)((k + 1) & 1), &mk_next))) return rc;
+      }
+      if ((rc = ahead_read(via_xchg, mk, &sc))) return rc;
+      f_x = f_cur;
+      g_z = g_value(sc);
+      if (k >= o->maxit || stop()) {                    // src/ProximalAlgorithms.jl:117
+        seq = seq_saved;
+        break;
+      }
+      f_cur = f_value(sc);                              // AUX = ||A x_{k+1} - b||^2
+      ix = ixn;
+      ixn = ixf;
+      izp = iz;
+      iz = izf;
+      ig = igo;
+      mk = mk_next;
+      ++k;
+    }
+    if (via_xchg) ctx->xchg_pending = 0;                // whatever was published last has been consumed or is discarded
+    x = X[ix];
+    x_next = X[ixn];
+    z = Z[iz];
+    z_prev = Z[izp];
+    grad = G[ig];
     return finish(out, k);
   }
 

@@ -65,7 +65,7 @@ def test_one_sweep_per_iteration_same_bits(T, nblk, mb, nb):
             got = _run(1, f, g, x0, Lf, tol, maxit, **kw)
             nl = ctx.launches() - l0
             assert got[1] == ref[1] and 1 <= got[1] <= maxit
-            assert nl <= 2 * got[1] + 8, "two launches per iteration (sweep + combine)"
+            assert nl <= 2 * (got[1] + 1) + 8, "two launches per iteration (sweep + combine), one iteration launched ahead"
             assert np.array_equal(got[0], ref[0], equal_nan=True)
             assert got[2] == ref[2], (got[2], ref[2])
             for u, v in zip(got[3], ref[3]):

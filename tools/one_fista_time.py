@@ -21,6 +21,7 @@ x0 = torch.zeros(nblk * nb, device="cuda")
 ctx = Context.get()
 L.check(ctx.lib.pb_ctx_set_option(ctx.h, L.PB_OPT_LSQ_FISTA, mode))
 s = pa.FastForwardBackward(maxit=200, tol=-1.0)
+s.pipeline = os.environ.get("PROXB200_NO_LOOKAHEAD", "0") != "1"      # A/B of the one-iteration look-ahead of the driver loop
 s(x0=x0, f=f, g=pa.NormL1(0.5), Lf=1100.0)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
@@ -28,4 +29,5 @@ z, it = s(x0=x0, f=f, g=pa.NormL1(0.5), Lf=1100.0)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 env = {k[10:]: v for k, v in os.environ.items() if k.startswith("PROXB200_LF_")}
+env["lookahead"] = s.pipeline
 print(f"mode {mode} {env}: {it / dt:.1f} it/s  {1e3 * dt / it:.4f} ms/it", flush=True)
