@@ -96,6 +96,19 @@ def _worker(rank, world, port, exchange, q):
             z, it = mk(tol=1e-7, maxit=5000)(x0=x0, f=f, g=pa_.NormL1(lam), comm=comm, n_global=n, **kw)
             out[name] = (it, z)
         if exchange == "device":
+            # the one-sweep FISTA kernel (csrc/lsq_fista.cu) forced on this small A: its combine kernel exchanges the scalar block in-kernel
+            # and the driver loop runs one iteration ahead through the exchange
+            from proxb200 import _lib as L_
+
+            blocks2, b2, lam2, Lf2 = _bd64_problem()
+            per2 = blocks2.shape[0] // world
+            f2 = pa_.BlockDiagLeastSquares.from_numpy(blocks2[rank * per2:(rank + 1) * per2], b2[rank * per2 * 64:(rank + 1) * per2 * 64], comm=comm)
+            L_.check(ctx.lib.pb_ctx_set_option(ctx.h, L_.PB_OPT_LSQ_FISTA, 1))
+            alg = pa_.FastForwardBackward(tol=1e-7, maxit=5000)
+            z, it = alg(x0=np.zeros(per2 * blocks2.shape[2]), f=f2, g=pa_.NormL1(lam2), comm=comm, n_global=blocks2.shape[0] * blocks2.shape[2], Lf=Lf2)
+            out["ffb_fixed_one_sweep"] = (it, z)
+            L_.check(ctx.lib.pb_ctx_set_option(ctx.h, L_.PB_OPT_LSQ_FISTA, 0))
+        if exchange == "device":
             # row-sharded PANOC + L-BFGS(5): every dot of the two-loop recursion is summed over the ranks inside its kernel
             for name, g_, kw in (("panoc_l1", pa_.NormL1(lam), {}), ("panoc_l21_fixed", pa_.NormL21(lam, 4), dict(Lf=Lf)),
                                  ("panoc_l1_lbfgs2", pa_.NormL1(lam), dict(directions=pa_.LBFGS(2)))):
@@ -118,6 +131,16 @@ def _worker(rank, world, port, exchange, q):
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def _bd64_problem():
+    """Block-diagonal Lasso whose blocks are tall enough (64 rows) for the one-sweep FISTA kernel."""
+    rng = np.random.default_rng(33)
+    nblk, mb, nb = 4, 64, 400
+    blocks = rng.standard_normal((nblk, mb, nb)) / np.sqrt(mb)
+    b = rng.standard_normal(nblk * mb)
+    lam = 0.1 * np.max(np.abs(np.einsum("bij,bi->bj", blocks, b.reshape(nblk, mb))))
+    return blocks, b, lam, 1.05 * max(np.linalg.norm(blocks[k], 2) ** 2 for k in range(nblk))
 
 
 def _dense_problem():
@@ -165,6 +188,12 @@ def test_two_rank_sharded_solve_equals_single_gpu(exchange):
         z_o, it_o = mk_o(np.zeros(nblk * nb), fo, o.NormL1(lam), tol=1e-7, maxit=5000, **kw)
         assert abs(it1 - it_o) <= max(2, it_o // 100) and np.max(np.abs(z1 - z_o)) <= 1e-8
     if exchange == "device":
+        blocks2, b2, lam2, Lf2 = _bd64_problem()
+        z1, it1 = pa.FastForwardBackward(tol=1e-7, maxit=5000)(x0=np.zeros(blocks2.shape[0] * blocks2.shape[2]), f=pa.BlockDiagLeastSquares.from_numpy(blocks2, b2),
+                                                               g=pa.NormL1(lam2), Lf=Lf2)          # two sweeps per iteration (A is small)
+        z2 = np.concatenate([res[r]["ffb_fixed_one_sweep"][1] for r in range(world)])
+        assert res[0]["ffb_fixed_one_sweep"][0] == res[1]["ffb_fixed_one_sweep"][0] == it1 and 3 < it1 < 5000
+        assert np.array_equal(z2, z1)
         Ad, bd, lamd, Lfd = _dense_problem()
         fd = pa.LeastSquares(Ad, bd)
         for name, kw in (("dense_ffb_adaptive", {}), ("dense_fb_adaptive", {}), ("dense_ffb_fixed", dict(Lf=Lfd))):

@@ -80,3 +80,36 @@ def test_matches_the_oracle_on_a_config1_like_problem():
     _mode(1)
     z, it = pa.FastForwardBackward(tol=1e-6)(x0=np.zeros(6 * 400, T), f=pa.BlockDiagLeastSquares.from_numpy(blocks, b), g=pa.NormL1(lam), Lf=Lf)
     assert it == it_o and np.max(np.abs(z - z_o)) <= 1e-9
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_look_ahead_through_the_exchange_and_without_it(T):
+    """The driver loop launches the sweep of iteration k+1 before it examines iteration k (csrc/solve.cu: run_ffb_bd_fista_ahead).  Three
+    ways for the scalars to reach the host -- synchronous read-back (no spare vectors), pinned slots + events (spares, no exchange), the
+    device exchange (spares, world 1) -- must stop at the same iteration with the same bits, for stops in the middle and at maxit."""
+    from proxb200.host import DeviceExchangeComm
+
+    blocks, b, lam, Lf = _problem(T, 5, 100, 2000, 77)
+    f = pa.BlockDiagLeastSquares.from_numpy(blocks, b)
+    x0 = np.zeros(5 * 2000, T)
+    g = pa.NormL1(lam)
+    for tol, maxit in ((T(1e-3), 500), (T(1e-5 if T == np.float64 else 1e-4), 500), (T(-1.0), 7), (T(-1.0), 1)):
+        runs = []
+        for how in ("sync", "slots", "exchange"):
+            _mode(1)
+            s = pa.FastForwardBackward(tol=tol, maxit=maxit, driver="native")
+            s.pipeline = how != "sync"
+            comm = DeviceExchangeComm(Context.get()) if how == "exchange" else None
+            try:
+                z, k = s(x0=x0, f=f, g=g, Lf=Lf, **({"comm": comm} if comm is not None else {}))
+            finally:
+                if comm is not None:
+                    comm.close()
+            st = s.last_state
+            runs.append((k, z, float(st.f_x), float(st.g_z), float(st.res_norm_inf), st.x.cpu().numpy().copy(), st.z_prev.cpu().numpy().copy(),
+                         st.grad_f_x.cpu().numpy().copy(), dict(s.last_parity)))
+        for r in runs[1:]:
+            assert r[0] == runs[0][0] and r[2:5] == runs[0][2:5] and r[8] == runs[0][8], (tol, maxit)
+            for u, v in zip((r[1],) + r[5:8], (runs[0][1],) + runs[0][5:8]):
+                assert np.array_equal(u, v, equal_nan=True)
+        assert 1 <= runs[0][0] <= maxit
