@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .host import Context, LocalComm, check_vec, pb_dtype, ptr, real_type, torch
+from .host import Context, DeviceExchangeComm, LocalComm, check_vec, pb_dtype, ptr, real_type, torch
 
 
 class Deferred:
@@ -158,7 +158,7 @@ class LeastSquares:
         self.ctx = ctx
         self.comm = comm or LocalComm()
         self.n_global, self.col_offset = n_global, col_offset
-        self.fused_gather = self.comm.size > 1 and n_global is not None and col_offset is not None and hasattr(self.comm, "timeout_s")
+        self.fused_gather = self.comm.size > 1 and n_global is not None and col_offset is not None and isinstance(self.comm, DeviceExchangeComm)
         if isinstance(A, t.Tensor):
             R = real_type(A.dtype)
             a_cm = A.to(ctx.device).t().contiguous()          # (n, m) row-major == A column-major
