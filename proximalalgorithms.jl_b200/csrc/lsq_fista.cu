@@ -6,6 +6,9 @@
 // With a FIXED stepsize the extrapolated point x+ is element-wise in grad, so the columns of A that produce grad_j also produce the
 // contribution a_j x+_j to the NEXT iteration's residual A x+ - b.  One kernel therefore sweeps A once per iteration:
 //
+// Two kernels share that plan: k_bd_fista_ws (default: the three phases below run on their own warps, tiles flow through them over
+// mbarriers) and k_bd_fista (phases one after the other behind CTA barriers; kept for row counts beyond the role layout of the first).
+//
 //   unit = (block k, column chunk c) -- the chunking of lsq_order.h --, one CTA, the chunk streamed through a TMA ring in tiles:
 //     A:  grad_j = a_j' r_k                      for the tile's columns      (order of k_gemv_t_sub: LPC lanes per column)
 //     B:  the fused step on those columns          -> z_j, x+_j, reductions    (StepElem, step_common.cuh; grad, z, x+ leave as 16-byte stores)
