@@ -253,3 +253,90 @@ def test_sharded_solve_world2_matches_unsharded_host_logic():
         host.Context.get = saved[0]
         for m, f in saved[1]:
             m.check_vec = f
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# N > 1 host path of a COLUMN-sharded dense A (C2, csrc/lsq_kernels.cu: k_gemv_n_combine_x): shard boundaries from
+# host.dense_shard_bounds (multiples of the column chunk of the residual order), per-chunk partial products, all-gather, fold of ALL
+# chunks in GLOBAL chunk order.  The kernels are stood in by numpy (any deterministic per-chunk partial will do: the property under test
+# is the fold rule); the exchange is gloo.  Aligned shards reproduce the unsharded float32 bits, which is what the device path asserts
+# on hardware (tests/test_gpu_local_world.py); a fold of per-rank sums in rank order -- the plain all-gather of rank partials -- does not.
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+def _chunk_partials(A, x, lo, hi, cc):
+    """float32 partial products of the chunks [lo, hi) (chunk-aligned lo), one row of the result per chunk."""
+    out = []
+    for c0 in range(lo, hi, cc):
+        c1 = min(hi, c0 + cc)
+        blk = np.ascontiguousarray(A[:, c0:c1]) * np.ascontiguousarray(x[c0:c1])[None, :]
+        s = np.zeros(A.shape[0], np.float32)
+        for j in range(c1 - c0):                   # sequential float32 chain per row, like one column lane of the kernel
+            s = (s + blk[:, j]).astype(np.float32)
+        out.append(s)
+    return np.stack(out) if out else np.zeros((0, A.shape[0]), np.float32)
+
+
+def _fold(parts):
+    s = parts[0].copy()
+    for p in parts[1:]:
+        s = (s + p).astype(np.float32)
+    return s
+
+
+def _dense_worker(rank, world, port, m, n, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from proxb200 import _lib as L
+        from proxb200.host import TorchDistComm, dense_shard_bounds
+
+        rng = np.random.default_rng(5)
+        A = rng.standard_normal((m, n)).astype(np.float32)
+        x = (rng.standard_normal(n) * 10.0 ** rng.integers(-3, 3, n)).astype(np.float32)
+        cc = int(L.lib().pb_lsq_dense_chunk_cols(L.PB_F32, m, n))
+        bounds = dense_shard_bounds(np.float32, m, n, world)
+        lo, hi = bounds[rank]
+        mine = _chunk_partials(A, x, lo, hi, cc)
+        nch = (n + cc - 1) // cc
+        per = max((b_[1] - b_[0] + cc - 1) // cc for b_ in bounds)
+        padded = np.zeros((per, m), np.float32)
+        padded[:mine.shape[0]] = mine
+        comm = TorchDistComm()
+        allp = comm.allgather_vector(torch.from_numpy(padded.reshape(-1))).numpy().reshape(world, per, m)
+        chunks = [allp[r][k] for r in range(world) for k in range((bounds[r][1] - bounds[r][0] + cc - 1) // cc)]
+        assert len(chunks) == nch
+        r_global_order = _fold(chunks)                                        # what k_gemv_n_combine_x does
+        rank_sums = [_fold([allp[r][k] for k in range((bounds[r][1] - bounds[r][0] + cc - 1) // cc)]) for r in range(world) if bounds[r][1] > bounds[r][0]]
+        r_rank_order = _fold(rank_sums)                                       # the all-gather of rank partials it replaces
+        q.put((rank, r_global_order, r_rank_order, cc, bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("m,n", [(40, 3000), (17, 10_000)])
+def test_column_sharded_dense_fold_rule_world2(lib_built, m, n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dense_worker, args=(r, world, port, m, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((m, n)).astype(np.float32)
+    x = (rng.standard_normal(n) * 10.0 ** rng.integers(-3, 3, n)).astype(np.float32)
+    cc, bounds = out[0][3], out[0][4]
+    whole = _fold(list(_chunk_partials(A, x, 0, n, cc)))                      # one GPU: all chunks in order
+    assert all(lo % cc == 0 for lo, _ in bounds) and bounds[0][0] == 0 and bounds[-1][1] == n
+    for _, r_global, r_rank, _, _ in out:
+        assert np.array_equal(r_global, whole)                                # same bits as unsharded, on every rank
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert not np.array_equal(out[0][2], whole)                               # rank sums folded in rank order: deterministic, but other bits
