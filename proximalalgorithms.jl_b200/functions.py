@@ -173,6 +173,14 @@ class LeastSquares:
         check_vec(self.b, self.m, a_cm.dtype)
         self.r = t.empty(self.m, dtype=a_cm.dtype, device=ctx.device)
         self.calls = 0
+        if self.fused_gather:
+            # the landing zone of the chunk partials is a fixed region of the exchange buffer (csrc/xchg.cuh: PB_XCHG_VEC_BYTES = 128 MB,
+            # [parity][global chunk][row] 8-byte words, two per double); a matrix that does not fit takes the NCCL all-gather instead --
+            # the same decision on every rank, since it depends on (m, n_global, dtype) only
+            cc = int(ctx.lib.pb_lsq_dense_chunk_cols(pb_dtype(R), self.m, int(n_global)))
+            nch = (int(n_global) + cc - 1) // cc
+            if 2 * nch * self.m * (np.dtype(R).itemsize // 4) * 8 > (128 << 20):
+                self.fused_gather = False
 
     def _residual(self, x):
         lib, ctx, dt = self.ctx.lib, self.ctx, pb_dtype(self.R)
